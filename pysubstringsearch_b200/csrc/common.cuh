@@ -1,0 +1,90 @@
+// common.cuh — shared helpers for libpss_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <atomic>
+
+#include "../../include/pss.h"
+
+namespace pss {
+
+// ---- error plumbing -----------------------------------------------------------------
+void set_error(const std::string &msg);
+int  fail(int code, const std::string &msg);
+
+extern std::atomic<long long> g_kernel_launches;
+inline void count_launch(int k = 1) { g_kernel_launches.fetch_add(k, std::memory_order_relaxed); }
+
+#define PSS_CUDA_TRY(expr)                                                                 \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            return ::pss::fail(_e == cudaErrorMemoryAllocation ? PSS_ERR_NOMEM : PSS_ERR_CUDA, \
+                               std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+        }                                                                                  \
+    } while (0)
+
+#define PSS_TRY(expr)                                                                      \
+    do {                                                                                   \
+        int _rc = (expr);                                                                  \
+        if (_rc != PSS_OK) return _rc;                                                     \
+    } while (0)
+
+// Check the launch of the kernel just enqueued.
+#define PSS_LAUNCH_CHECK()                                                                 \
+    do {                                                                                   \
+        ::pss::count_launch();                                                             \
+        PSS_CUDA_TRY(cudaGetLastError());                                                  \
+    } while (0)
+
+int default_device();
+int sm_count(int device);
+
+// ---- device helpers -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Streaming (read-once) loads: keep them out of L1 so the staging tiles own it.
+__device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ld_stream_u128(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+static inline int bit_width_u64(uint64_t v) {
+    int b = 0;
+    while (v) { ++b; v >>= 1; }
+    return b;
+}
+
+static inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace pss

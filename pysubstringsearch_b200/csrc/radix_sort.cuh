@@ -1,0 +1,71 @@
+// radix_sort.cuh — hand-written onesweep LSD radix sort over (key u64, value u32) records.
+//
+// One upfront histogram kernel computes the 256-bin histograms of every 8-bit digit in
+// [begin_bit, end_bit); each digit then costs ONE pass over the data: a tile (CTA) ranks
+// its records with warp-level match_any, publishes its per-digit counts, resolves its
+// global offsets by decoupled look-back over the preceding tiles, stages the records in
+// shared memory in digit order and writes them out in coalesced per-digit runs.
+// Digits whose histogram has a single non-empty bin are skipped on the host.
+//
+// This replaces (as the inner engine of a prefix-doubling builder) the serial induced
+// sorting scans of the reference's libsais (src/libsais/libsais.c:2105, :2936, :4565,
+// :5194); it is not a translation of them.
+#pragma once
+
+#include "common.cuh"
+
+namespace pss {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX      = 1 << RADIX_BITS;
+constexpr int MAX_PASSES = 8;
+
+// Tile geometry of the pass kernel (tuned on B200).
+constexpr int PASS_THREADS = 512;
+constexpr int PASS_IPT     = 8;
+constexpr int PASS_TILE    = PASS_THREADS * PASS_IPT;
+
+struct SortProfile {
+    bool  timed    = false;  // in: record CUDA events around the histogram and every pass
+    int   n_passes = 0;      // out: passes executed (constant digits are skipped)
+    int   shift[MAX_PASSES] = {};
+    float ms[MAX_PASSES]    = {};   // valid when timed
+    float hist_ms = 0.f;            // valid when timed
+};
+
+class RadixSorter {
+public:
+    RadixSorter() = default;
+    ~RadixSorter() { release(); }
+    RadixSorter(const RadixSorter &) = delete;
+    RadixSorter &operator=(const RadixSorter &) = delete;
+
+    int  init(int device);
+    int  ensure(int64_t n);  // workspace for up to n records
+    void release();
+
+    // Sorts records by key bits [begin_bit, end_bit), stable.  iota_vals means the input
+    // values are 0..n-1 and `vals` is only scratch (they are generated on the fly in the
+    // first executed pass).  *in_alt tells where the result is.  prof (optional) receives
+    // the executed pass list and, if prof->timed, per-pass CUDA-event durations.
+    // Synchronises the stream before returning.
+    int sort(uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, uint32_t *vals_alt,
+             uint32_t n, int begin_bit, int end_bit, bool iota_vals, cudaStream_t stream,
+             bool *in_alt, SortProfile *prof);
+
+    int device() const { return device_; }
+
+private:
+    int       device_        = -1;
+    int       num_sms_       = 0;
+    int64_t   tile_capacity_ = 0;
+    uint32_t *d_hist_        = nullptr;  // [MAX_PASSES][RADIX]
+    uint32_t *d_bin_base_    = nullptr;  // [MAX_PASSES][RADIX]
+    uint32_t *d_tile_state_  = nullptr;  // [tile_capacity][RADIX]
+    uint32_t *d_ctrl_        = nullptr;  // [0..8) tickets, [8] error flag, [16..24) trivial flags
+    uint32_t *h_ctrl_        = nullptr;  // pinned mirror of d_ctrl_
+    cudaEvent_t ev_[2 * MAX_PASSES + 2] = {};
+    bool      ev_ready_      = false;
+};
+
+}  // namespace pss

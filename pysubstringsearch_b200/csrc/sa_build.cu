@@ -1,0 +1,532 @@
+// sa_build.cu — prefix-doubling suffix-array builder for sm_100a (see sa_build.cuh).
+#include "sa_build.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+namespace pss {
+
+namespace {
+
+// d_small_ layout (32-bit words)
+constexpr int SM_PRESENCE = 0;    // [0..8)   256-bit set of byte values present in the text
+constexpr int SM_SCALARS  = 8;    // [8..16)  [8] = active suffixes after the current re-rank
+constexpr int SM_LUT      = 16;   // [16..144) 256 x u16: byte value → dense code (1..sigma)
+constexpr int SM_WORDS    = 144;
+
+// ------------------------------------------------------------------------------------
+// Alphabet: which byte values occur (a 256-bit presence set is all the packing needs).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+presence_kernel(const uint8_t *__restrict__ text, uint32_t n, uint32_t *__restrict__ presence) {
+    __shared__ uint32_t s_seen[256];
+    s_seen[threadIdx.x] = 0;
+    __syncthreads();
+    // 16-byte vector body between the first and last 16-byte boundary; ragged ends by
+    // one thread.
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(text);
+    uint32_t head = (uint32_t)((16 - (addr & 15)) & 15);
+    if (head > n) head = n;
+    const uint32_t nvec = (n - head) / 16;
+    const uint4 *vec    = reinterpret_cast<const uint4 *>(text + head);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
+        uint4 v = ld_stream_u128(vec + i);
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            s_seen[w[q] & 0xFF]         = 1;
+            s_seen[(w[q] >> 8) & 0xFF]  = 1;
+            s_seen[(w[q] >> 16) & 0xFF] = 1;
+            s_seen[w[q] >> 24]          = 1;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (uint32_t i = 0; i < head; ++i) s_seen[text[i]] = 1;
+        for (uint32_t i = head + nvec * 16; i < n; ++i) s_seen[text[i]] = 1;
+    }
+    __syncthreads();
+    if (s_seen[threadIdx.x]) atomicOr(&presence[threadIdx.x >> 5], 1u << (threadIdx.x & 31));
+}
+
+// ------------------------------------------------------------------------------------
+// Round 0 keys: key(i) = codes of T[i .. i+m) packed big-endian, b bits each, 0 past end.
+// ------------------------------------------------------------------------------------
+constexpr int KG_THREADS = 256;
+constexpr int KG_IPT     = 16;
+constexpr int KG_TILE    = KG_THREADS * KG_IPT;
+
+__global__ void __launch_bounds__(KG_THREADS)
+keygen_kernel(const uint8_t *__restrict__ text, uint32_t n, const uint16_t *__restrict__ lut, int b, int m,
+              uint64_t *__restrict__ keys) {
+    __shared__ uint16_t s_lut[256];
+    __shared__ uint16_t s_code[KG_TILE + 64];
+    __shared__ uint64_t s_key[KG_TILE + KG_TILE / KG_IPT];  // one pad word per thread row
+    const uint32_t tid = threadIdx.x;
+    const uint32_t base = blockIdx.x * KG_TILE;
+    s_lut[tid] = lut[tid];
+    __syncthreads();
+    for (uint32_t i = tid; i < (uint32_t)(KG_TILE + m); i += KG_THREADS) {
+        uint32_t pos = base + i;
+        s_code[i] = pos < n ? s_lut[text[pos]] : (uint16_t)0;
+    }
+    __syncthreads();
+    const uint64_t mask = (m * b >= 64) ? ~0ull : ((1ull << (m * b)) - 1ull);
+    const uint32_t r0 = tid * KG_IPT;
+    uint64_t w = 0;
+    for (int j = 0; j < m; ++j) w = (w << b) | s_code[r0 + j];
+#pragma unroll
+    for (int j = 0; j < KG_IPT; ++j) {
+        s_key[tid * (KG_IPT + 1) + j] = w;
+        w = ((w << b) & mask) | s_code[r0 + j + m];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < KG_IPT; ++j) {
+        uint32_t i = j * KG_THREADS + tid;
+        if (base + i < n) keys[base + i] = s_key[(i / KG_IPT) * (KG_IPT + 1) + (i % KG_IPT)];
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Round r >= 1 keys: (group rank << rbits) | rank of suffix i + h (0 past the end).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gather_kernel(const uint32_t *__restrict__ idx, const uint32_t *__restrict__ grp,
+              const uint32_t *__restrict__ isa, uint32_t n, uint32_t h, int rbits, uint32_t n_active,
+              uint64_t *__restrict__ keys) {
+    constexpr int U = 4;
+    const uint32_t base = (blockIdx.x * 256 * U) + threadIdx.x;
+    uint32_t i[U], g[U], r[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        uint32_t k = base + u * 256;
+        i[u] = k < n_active ? ld_stream_u32(idx + k) : 0u;
+        g[u] = k < n_active ? ld_stream_u32(grp + k) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        uint32_t k = base + u * 256;
+        uint64_t j = (uint64_t)i[u] + h;
+        r[u] = (k < n_active && j < n) ? __ldg(isa + j) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        uint32_t k = base + u * 256;
+        if (k < n_active) keys[k] = ((uint64_t)g[u] << rbits) | r[u];
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Segmented re-rank after a sort.  For sorted position k (old group rank g = key >> gs):
+//   A(k) = last k' <= k that starts an old group,  B(k) = last k' <= k that starts a new
+//   group (new group = run of equal full keys).  SA position p = g + (k - A), new group
+//   rank = g + (B - A).  A suffix alone in its new group is final: SA[p] = i.  The rest
+//   are compacted (order preserved) into the next round's active set.
+// Implemented as reduce → scan of tile aggregates → apply over tiles of 2048 records.
+// ------------------------------------------------------------------------------------
+constexpr int RR_THREADS = 256;
+constexpr int RR_IPT     = 8;
+constexpr int RR_TILE    = RR_THREADS * RR_IPT;
+
+struct Tup {
+    uint32_t a, b, s;  // a/b: (position + 1) of the last old/new head seen, 0 = none; s: kept count
+};
+__device__ __forceinline__ Tup tup_comb(const Tup &x, const Tup &y) {
+    Tup r;
+    r.a = max(x.a, y.a);
+    r.b = max(x.b, y.b);
+    r.s = x.s + y.s;
+    return r;
+}
+__device__ __forceinline__ Tup tup_shfl_up(const Tup &x, int o) {
+    Tup r;
+    r.a = __shfl_up_sync(0xffffffffu, x.a, o);
+    r.b = __shfl_up_sync(0xffffffffu, x.b, o);
+    r.s = __shfl_up_sync(0xffffffffu, x.s, o);
+    return r;
+}
+
+// Exclusive scan of one Tup per thread across the block; returns the exclusive prefix and
+// writes the block total to *total (valid in every thread).  s_warp: one Tup per warp.
+template <int THREADS>
+__device__ __forceinline__ Tup block_excl_scan(Tup v, Tup *s_warp, Tup *total) {
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    Tup incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        Tup y = tup_shfl_up(incl, o);
+        if (lane >= (uint32_t)o) incl = tup_comb(y, incl);
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    Tup pre = {0, 0, 0};
+    Tup tot = {0, 0, 0};
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) {
+        Tup t = s_warp[w];
+        if ((uint32_t)w < warp) pre = tup_comb(pre, t);
+        tot = tup_comb(tot, t);
+    }
+    Tup up = tup_shfl_up(incl, 1);
+    if (lane > 0) pre = tup_comb(pre, up);
+    *total = tot;
+    __syncthreads();
+    return pre;
+}
+
+// Sorted keys of a tile (+ one halo record each side) in shared memory, padded so that
+// a thread's 8 consecutive records do not collide on banks.  Local index u = k - base + 1.
+struct RerankTile {
+    uint64_t k[RR_TILE + 2 + (RR_TILE + 2) / 8 + 1];
+    __device__ __forceinline__ static uint32_t slot(uint32_t u) { return u + (u >> 3); }
+};
+
+__device__ __forceinline__ void rerank_load(RerankTile &t, const uint64_t *__restrict__ keys, uint32_t base,
+                                            uint32_t n_active) {
+    for (uint32_t u = threadIdx.x; u < RR_TILE + 2; u += RR_THREADS) {
+        int64_t k = (int64_t)base + u - 1;
+        uint64_t v = 0;
+        if (k >= 0 && k < (int64_t)n_active) v = ld_stream_u64(keys + k);
+        t.k[RerankTile::slot(u)] = v;
+    }
+    __syncthreads();
+}
+
+// Flags of sorted record k (u = local index + 1): bit0 old head, bit1 new head, bit2 kept.
+__device__ __forceinline__ uint32_t rerank_flags(const RerankTile &t, uint32_t u, uint32_t k, uint32_t n_active,
+                                                 int gs, bool first) {
+    uint64_t prev = t.k[RerankTile::slot(u - 1)];
+    uint64_t cur  = t.k[RerankTile::slot(u)];
+    uint64_t next = t.k[RerankTile::slot(u + 1)];
+    bool hn  = (k == 0) || (cur != prev);
+    bool ho  = (k == 0) || (!first && ((cur >> gs) != (prev >> gs)));
+    bool nhn = (k + 1 == n_active) || (next != cur);
+    bool keep = !(hn && nhn);
+    return (ho ? 1u : 0u) | (hn ? 2u : 0u) | (keep ? 4u : 0u);
+}
+
+__global__ void __launch_bounds__(RR_THREADS)
+rerank_reduce_kernel(const uint64_t *__restrict__ keys, uint32_t n_active, int gs, int first,
+                     uint32_t *__restrict__ tile_aggr) {
+    __shared__ RerankTile tile;
+    __shared__ Tup s_warp[RR_THREADS / 32];
+    const uint32_t base = blockIdx.x * RR_TILE;
+    rerank_load(tile, keys, base, n_active);
+    Tup agg = {0, 0, 0};
+#pragma unroll
+    for (int e = 0; e < RR_IPT; ++e) {
+        uint32_t loc = threadIdx.x * RR_IPT + e;
+        uint32_t k   = base + loc;
+        if (k < n_active) {
+            uint32_t f = rerank_flags(tile, loc + 1, k, n_active, gs, first != 0);
+            if (f & 1u) agg.a = k + 1;
+            if (f & 2u) agg.b = k + 1;
+            agg.s += (f >> 2) & 1u;
+        }
+    }
+    Tup total;
+    (void)block_excl_scan<RR_THREADS>(agg, s_warp, &total);
+    if (threadIdx.x == 0) {
+        tile_aggr[blockIdx.x * 3 + 0] = total.a;
+        tile_aggr[blockIdx.x * 3 + 1] = total.b;
+        tile_aggr[blockIdx.x * 3 + 2] = total.s;
+    }
+}
+
+constexpr int RS_THREADS = 1024;
+__global__ void __launch_bounds__(RS_THREADS)
+rerank_scan_kernel(uint32_t *__restrict__ tile_aggr, uint32_t tiles, uint32_t *__restrict__ scalars) {
+    __shared__ Tup s_warp[RS_THREADS / 32];
+    const uint32_t per = (tiles + RS_THREADS - 1) / RS_THREADS;
+    const uint32_t lo  = min(tiles, threadIdx.x * per);
+    const uint32_t hi  = min(tiles, lo + per);
+    Tup agg = {0, 0, 0};
+    for (uint32_t t = lo; t < hi; ++t) {
+        Tup v = {tile_aggr[t * 3 + 0], tile_aggr[t * 3 + 1], tile_aggr[t * 3 + 2]};
+        agg = tup_comb(agg, v);
+    }
+    Tup total;
+    Tup run = block_excl_scan<RS_THREADS>(agg, s_warp, &total);
+    for (uint32_t t = lo; t < hi; ++t) {
+        Tup v = {tile_aggr[t * 3 + 0], tile_aggr[t * 3 + 1], tile_aggr[t * 3 + 2]};
+        tile_aggr[t * 3 + 0] = run.a;
+        tile_aggr[t * 3 + 1] = run.b;
+        tile_aggr[t * 3 + 2] = run.s;
+        run = tup_comb(run, v);
+    }
+    if (threadIdx.x == 0) scalars[0] = total.s;
+}
+
+__global__ void __launch_bounds__(RR_THREADS)
+rerank_apply_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t n_active,
+                    int gs, int first, const uint32_t *__restrict__ tile_prefix, uint32_t *__restrict__ isa,
+                    int32_t *__restrict__ sa, uint32_t *__restrict__ out_idx, uint32_t *__restrict__ out_grp) {
+    __shared__ RerankTile tile;
+    __shared__ Tup s_warp[RR_THREADS / 32];
+    const uint32_t base = blockIdx.x * RR_TILE;
+    rerank_load(tile, keys, base, n_active);
+
+    uint32_t flags[RR_IPT];
+    uint32_t idx[RR_IPT];
+    Tup agg = {0, 0, 0};
+#pragma unroll
+    for (int e = 0; e < RR_IPT; ++e) {
+        uint32_t loc = threadIdx.x * RR_IPT + e;
+        uint32_t k   = base + loc;
+        flags[e] = 0;
+        idx[e]   = 0;
+        if (k < n_active) {
+            uint32_t f = rerank_flags(tile, loc + 1, k, n_active, gs, first != 0);
+            flags[e]   = f | 8u;  // bit3: record exists
+            idx[e]     = ld_stream_u32(vals + k);
+            if (f & 1u) agg.a = k + 1;
+            if (f & 2u) agg.b = k + 1;
+            agg.s += (f >> 2) & 1u;
+        }
+    }
+    Tup total;
+    Tup run = block_excl_scan<RR_THREADS>(agg, s_warp, &total);
+    Tup pre = {tile_prefix[blockIdx.x * 3 + 0], tile_prefix[blockIdx.x * 3 + 1], tile_prefix[blockIdx.x * 3 + 2]};
+    run = tup_comb(pre, run);
+
+#pragma unroll
+    for (int e = 0; e < RR_IPT; ++e) {
+        if (!(flags[e] & 8u)) continue;
+        uint32_t loc = threadIdx.x * RR_IPT + e;
+        uint32_t k   = base + loc;
+        uint32_t f   = flags[e];
+        if (f & 1u) run.a = k + 1;
+        if (f & 2u) run.b = k + 1;
+        const uint32_t A = run.a - 1, B = run.b - 1;
+        const uint32_t g = first ? 0u : (uint32_t)(tile.k[RerankTile::slot(loc + 1)] >> gs);
+        const uint32_t p  = g + (k - A);   // final SA slot of this record inside its old group
+        const uint32_t ng = g + (B - A);   // rank of its new group = SA slot of the group's head
+        if (f & 4u) {
+            const uint32_t c = run.s++;
+            out_idx[c] = idx[e];
+            out_grp[c] = ng;
+            if (first || ng != g) isa[idx[e]] = ng + 1;
+        } else {
+            sa[p] = (int32_t)idx[e];
+            if (first || p != g) isa[idx[e]] = p + 1;
+        }
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------
+int SaBuilder::init(int device, int64_t max_n) {
+    if (device_ >= 0) return PSS_OK;
+    if (device < 0) device = default_device();
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(PSS_ERR_CUDA, "no CUDA device available (libpss_b200 has no CPU fallback)");
+    if (device >= ndev) return fail(PSS_ERR_ARG, "device index out of range");
+    PSS_CUDA_TRY(cudaSetDevice(device));
+    device_ = device;
+    PSS_CUDA_TRY(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    PSS_CUDA_TRY(cudaEventCreate(&ev_begin_));
+    PSS_CUDA_TRY(cudaEventCreate(&ev_end_));
+    PSS_CUDA_TRY(cudaMalloc(&d_small_, SM_WORDS * sizeof(uint32_t)));
+    PSS_CUDA_TRY(cudaMallocHost(&h_small_, SM_WORDS * sizeof(uint32_t)));
+    PSS_TRY(sorter_.init(device_));
+    if (max_n > 0) PSS_TRY(ensure(max_n));
+    return PSS_OK;
+}
+
+int SaBuilder::ensure(int64_t n) {
+    if (n <= cap_) return PSS_OK;
+    PSS_CUDA_TRY(cudaSetDevice(device_));
+    cudaFree(keys_a_); cudaFree(keys_b_); cudaFree(vals_a_); cudaFree(vals_b_);
+    cudaFree(grp_); cudaFree(isa_); cudaFree(tile_aggr_);
+    keys_a_ = keys_b_ = nullptr; vals_a_ = vals_b_ = grp_ = isa_ = tile_aggr_ = nullptr;
+    cap_ = 0;
+    int64_t cap = std::max<int64_t>(n, 1 << 16);
+    PSS_CUDA_TRY(cudaMalloc(&keys_a_, cap * sizeof(uint64_t)));
+    PSS_CUDA_TRY(cudaMalloc(&keys_b_, cap * sizeof(uint64_t)));
+    PSS_CUDA_TRY(cudaMalloc(&vals_a_, cap * sizeof(uint32_t)));
+    PSS_CUDA_TRY(cudaMalloc(&vals_b_, cap * sizeof(uint32_t)));
+    PSS_CUDA_TRY(cudaMalloc(&grp_, cap * sizeof(uint32_t)));
+    PSS_CUDA_TRY(cudaMalloc(&isa_, cap * sizeof(uint32_t)));
+    PSS_CUDA_TRY(cudaMalloc(&tile_aggr_, (size_t)div_up(cap, RR_TILE) * 3 * sizeof(uint32_t)));
+    PSS_TRY(sorter_.ensure(cap));
+    cap_ = cap;
+    return PSS_OK;
+}
+
+int SaBuilder::ensure_io(int64_t n) {
+    if (n <= io_cap_) return PSS_OK;
+    PSS_CUDA_TRY(cudaSetDevice(device_));
+    cudaFree(d_text_); cudaFree(d_sa_);
+    d_text_ = nullptr; d_sa_ = nullptr; io_cap_ = 0;
+    int64_t cap = std::max<int64_t>(n, 1 << 16);
+    PSS_CUDA_TRY(cudaMalloc(&d_text_, cap + 64));
+    PSS_CUDA_TRY(cudaMalloc(&d_sa_, cap * sizeof(int32_t)));
+    io_cap_ = cap;
+    return PSS_OK;
+}
+
+void SaBuilder::release() {
+    if (device_ < 0) return;
+    cudaSetDevice(device_);
+    cudaFree(keys_a_); cudaFree(keys_b_); cudaFree(vals_a_); cudaFree(vals_b_);
+    cudaFree(grp_); cudaFree(isa_); cudaFree(tile_aggr_); cudaFree(d_small_);
+    cudaFree(d_text_); cudaFree(d_sa_);
+    if (h_small_) cudaFreeHost(h_small_);
+    if (ev_begin_) cudaEventDestroy(ev_begin_);
+    if (ev_end_) cudaEventDestroy(ev_end_);
+    if (stream_) cudaStreamDestroy(stream_);
+    sorter_.release();
+    keys_a_ = keys_b_ = nullptr; vals_a_ = vals_b_ = grp_ = isa_ = tile_aggr_ = d_small_ = nullptr;
+    h_small_ = nullptr; d_text_ = nullptr; d_sa_ = nullptr; stream_ = nullptr;
+    ev_begin_ = ev_end_ = nullptr;
+    cap_ = io_cap_ = 0;
+    device_ = -1;
+}
+
+int SaBuilder::build_device(const uint8_t *d_text, int32_t n, int32_t *d_sa, cudaStream_t stream) {
+    if (device_ < 0) return fail(PSS_ERR_ARG, "builder not initialised");
+    if (n < 0 || (n > 0 && (!d_text || !d_sa))) return fail(PSS_ERR_ARG, "bad build arguments");
+    if ((int64_t)n >= (1ll << 30)) return fail(PSS_ERR_ARG, "n must be < 2^30 (container stores 4n in a u32)");
+    std::memset(&stats_, 0, sizeof(stats_));
+    pass_stats_.clear();
+    stats_.n = n;
+    if (n == 0) return PSS_OK;
+    PSS_CUDA_TRY(cudaSetDevice(device_));
+    cudaStream_t s = stream ? stream : stream_;
+    const long long launches0 = g_kernel_launches.load();
+    if (n == 1) {
+        PSS_CUDA_TRY(cudaMemsetAsync(d_sa, 0, sizeof(int32_t), s));
+        PSS_CUDA_TRY(cudaStreamSynchronize(s));
+        return PSS_OK;
+    }
+    PSS_TRY(ensure(n));
+    const uint32_t un = (uint32_t)n;
+
+    PSS_CUDA_TRY(cudaEventRecord(ev_begin_, s));
+
+    // ---- alphabet → dense codes -------------------------------------------------------
+    PSS_CUDA_TRY(cudaMemsetAsync(d_small_, 0, SM_WORDS * sizeof(uint32_t), s));
+    {
+        int grid = (int)std::min<int64_t>(div_up(n, 256 * 64), (int64_t)sm_count(device_) * 8);
+        presence_kernel<<<std::max(grid, 1), 256, 0, s>>>(d_text, un, d_small_ + SM_PRESENCE);
+        PSS_LAUNCH_CHECK();
+    }
+    PSS_CUDA_TRY(cudaMemcpyAsync(h_small_, d_small_, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    PSS_CUDA_TRY(cudaStreamSynchronize(s));
+    int sigma = 0;
+    uint16_t *lut = reinterpret_cast<uint16_t *>(h_small_ + SM_LUT);
+    for (int c = 0; c < 256; ++c) {
+        bool present = (h_small_[SM_PRESENCE + (c >> 5)] >> (c & 31)) & 1u;
+        lut[c] = present ? (uint16_t)(++sigma) : (uint16_t)0;
+    }
+    const int b = bit_width_u64((uint64_t)sigma);  // codes 1..sigma, 0 = past the end
+    int m = 64 / b;
+    if (const char *e = std::getenv("PSS_H0")) {
+        int v = std::atoi(e);
+        if (v >= 1 && v <= 64 / b) m = v;
+    }
+    if ((int64_t)m > (int64_t)n) m = n;  // no point packing past the text
+    stats_.sigma = sigma;
+    stats_.bits_per_symbol = b;
+    stats_.h0 = m;
+    PSS_CUDA_TRY(cudaMemcpyAsync(d_small_ + SM_LUT, h_small_ + SM_LUT, 512, cudaMemcpyHostToDevice, s));
+
+    // ---- round 0: packed-prefix keys, sort, rank ---------------------------------------
+    keygen_kernel<<<(unsigned)div_up(n, KG_TILE), KG_THREADS, 0, s>>>(
+        d_text, un, reinterpret_cast<const uint16_t *>(d_small_ + SM_LUT), b, m, keys_a_);
+    PSS_LAUNCH_CHECK();
+
+    SortProfile prof;
+    prof.timed = profiling_;
+    auto record_passes = [&](int round, uint32_t n_rec) {
+        stats_.n_passes += prof.n_passes;
+        for (int p = 0; p < prof.n_passes; ++p) {
+            stats_.records_sorted += n_rec;
+            stats_.sort_ms += prof.ms[p];
+            if (profiling_ && (int)pass_stats_.size() < PSS_MAX_PASS_STATS) {
+                pss_pass_stat ps = {};
+                ps.round = round; ps.pass = p; ps.shift = prof.shift[p];
+                ps.n_records = n_rec; ps.ms = prof.ms[p];
+                pass_stats_.push_back(ps);
+            }
+        }
+    };
+
+    const int rbits = bit_width_u64((uint64_t)un);       // ranks 0..n  (0 = past the end)
+    const int gbits = bit_width_u64((uint64_t)un - 1);   // group ranks 0..n-1
+    bool in_alt = false;
+    stats_.active_per_round[0] = n;
+    PSS_TRY(sorter_.sort(keys_a_, keys_b_, vals_a_, vals_b_, un, 0, m * b, /*iota=*/true, s, &in_alt, &prof));
+    record_passes(0, un);
+
+    uint32_t  n_active = un;
+    uint32_t *v_sorted = in_alt ? vals_b_ : vals_a_;
+    uint32_t *v_free   = in_alt ? vals_a_ : vals_b_;
+    uint64_t *k_sorted = in_alt ? keys_b_ : keys_a_;
+    auto rerank = [&](bool first) -> int {
+        const uint32_t tiles = (uint32_t)div_up(n_active, RR_TILE);
+        rerank_reduce_kernel<<<tiles, RR_THREADS, 0, s>>>(k_sorted, n_active, rbits, first ? 1 : 0, tile_aggr_);
+        PSS_LAUNCH_CHECK();
+        rerank_scan_kernel<<<1, RS_THREADS, 0, s>>>(tile_aggr_, tiles, d_small_ + SM_SCALARS);
+        PSS_LAUNCH_CHECK();
+        rerank_apply_kernel<<<tiles, RR_THREADS, 0, s>>>(k_sorted, v_sorted, n_active, rbits, first ? 1 : 0,
+                                                         tile_aggr_, isa_, d_sa, v_free, grp_);
+        PSS_LAUNCH_CHECK();
+        PSS_CUDA_TRY(cudaMemcpyAsync(h_small_ + SM_SCALARS, d_small_ + SM_SCALARS, sizeof(uint32_t),
+                                     cudaMemcpyDeviceToHost, s));
+        PSS_CUDA_TRY(cudaStreamSynchronize(s));
+        n_active = h_small_[SM_SCALARS];
+        return PSS_OK;
+    };
+    PSS_TRY(rerank(true));
+
+    // ---- doubling rounds ------------------------------------------------------------------
+    uint64_t h = (uint64_t)m;
+    int round = 0;
+    while (n_active > 0) {
+        ++round;
+        if (round >= 63 || h >= (uint64_t)n * 2) return fail(PSS_ERR_CUDA, "prefix doubling failed to converge");
+        stats_.active_per_round[round] = n_active;
+        uint32_t *v_in = v_free;  // compacted active suffix indices written by the last re-rank
+        uint32_t *v_alt = (v_in == vals_a_) ? vals_b_ : vals_a_;
+        gather_kernel<<<(unsigned)div_up(n_active, 256 * 4), 256, 0, s>>>(v_in, grp_, isa_, un, (uint32_t)std::min<uint64_t>(h, un),
+                                                                         rbits, n_active, keys_a_);
+        PSS_LAUNCH_CHECK();
+        PSS_TRY(sorter_.sort(keys_a_, keys_b_, v_in, v_alt, n_active, 0, rbits + gbits, /*iota=*/false, s, &in_alt,
+                             &prof));
+        record_passes(round, n_active);
+        k_sorted = in_alt ? keys_b_ : keys_a_;
+        v_sorted = in_alt ? v_alt : v_in;
+        v_free   = in_alt ? v_in : v_alt;
+        PSS_TRY(rerank(false));
+        h *= 2;
+    }
+    stats_.rounds = round;
+
+    PSS_CUDA_TRY(cudaEventRecord(ev_end_, s));
+    PSS_CUDA_TRY(cudaEventSynchronize(ev_end_));
+    PSS_CUDA_TRY(cudaEventElapsedTime(&stats_.total_ms, ev_begin_, ev_end_));
+    stats_.n_pass_stats = (int32_t)pass_stats_.size();
+    stats_.n_kernel_launches = (int32_t)(g_kernel_launches.load() - launches0);
+    return PSS_OK;
+}
+
+int SaBuilder::build_host(const uint8_t *h_text, int32_t n, int32_t *h_sa) {
+    if (n < 0 || (n > 0 && (!h_text || !h_sa))) return fail(PSS_ERR_ARG, "bad build arguments");
+    if (n == 0) return PSS_OK;
+    PSS_CUDA_TRY(cudaSetDevice(device_));
+    PSS_TRY(ensure_io(n));
+    PSS_CUDA_TRY(cudaMemcpyAsync(d_text_, h_text, (size_t)n, cudaMemcpyHostToDevice, stream_));
+    PSS_TRY(build_device(d_text_, n, d_sa_, stream_));
+    PSS_CUDA_TRY(cudaMemcpyAsync(h_sa, d_sa_, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+    PSS_CUDA_TRY(cudaStreamSynchronize(stream_));
+    return PSS_OK;
+}
+
+}  // namespace pss
