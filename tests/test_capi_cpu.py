@@ -1,0 +1,114 @@
+"""CPU tests of the C-ABI library and the Python boundary: it loads, exports what
+include/pss.h declares, and its host-side logic (argument checks, error mapping, container
+validation) behaves — no compute call needs a GPU here."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import pytest
+
+from tests.conftest import HAVE_GPU, ROOT
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "pss.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(pss_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol(pss):
+    syms = declared_symbols()
+    assert len(syms) >= 29
+    for s in syms:
+        assert hasattr(pss.lib, s), "libpss_b200.so does not export %s" % s
+
+
+def test_version_and_device_count(pss):
+    assert b"sm_100a" in pss.lib.pss_version()
+    assert pss.lib.pss_device_count() >= 0
+
+
+def test_libsais_argument_contract(pss):
+    # libsais.c:6599-6602: NULL / negative arguments → -1, before any device work
+    assert pss.lib.pss_libsais(None, None, 5, 0, None) == -1
+    buf = (C.c_uint8 * 4)()
+    sa = (C.c_int32 * 4)()
+    assert pss.lib.pss_libsais(buf, sa, -1, 0, None) == -1
+    assert pss.lib.pss_libsais(buf, sa, 4, -1, None) == -1
+    assert pss.lib.pss_libsais(buf, sa, 0, 0, None) == 0      # n == 0 is a no-op
+
+
+def test_reader_missing_file(pss):
+    h = C.c_void_p()
+    rc = pss.lib.pss_reader_open(b"/nonexistent/dir/missing.idx", C.byref(h))
+    assert rc == -5 and "No such file" in pss.err()
+
+
+def test_reader_rejects_truncated_container(pss):
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "bad.idx").encode()
+        h = C.c_void_p()
+        good = bytes.fromhex("0300000061620a0c000000020000000000000001000000")
+        for cut in (2, 6, 9, 15, len(good) - 1):
+            open(p, "wb").write(good[:cut])
+            assert pss.lib.pss_reader_open(p, C.byref(h)) == -7, cut
+        open(p, "wb").write(good[:7] + bytes.fromhex("08000000") + good[11:])   # sa_bytes != 4n
+        assert pss.lib.pss_reader_open(p, C.byref(h)) == -7
+
+
+def test_writer_host_logic(pss):
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "w.idx")
+        w = pss.Writer(p, max_chunk_len=4)
+        assert w.add_entry("12345") == -6 and "too big" in pss.err()
+        assert w.add_entry("123") == 0
+        if not HAVE_GPU:
+            # the flush needs the GPU builder: must fail loudly, never fall back to a CPU path
+            assert w.add_entry("x") == -3
+            assert "no CUDA device" in pss.err() or "CUDA" in pss.err()
+            assert w.finalize() == -3
+        h = C.c_void_p()
+        assert pss.lib.pss_writer_open(os.path.join(d, "no/such/dir/x.idx").encode(), -1, C.byref(h)) == -5
+        assert w.add_entries_from_file_lines(os.path.join(d, "missing.txt")) == -5
+
+
+def test_python_module_surface():
+    import pysubstringsearch
+    import pysubstringsearch_b200 as m
+    assert pysubstringsearch.Writer is m.Writer and pysubstringsearch.Reader is m.Reader
+    for cls, names in ((m.Writer, ["add_entries_from_file_lines", "add_entry", "dump_data", "finalize"]),
+                       (m.Reader, ["search", "search_multiple"])):
+        for n in names:
+            assert callable(getattr(cls, n))
+    with pytest.raises(FileNotFoundError):
+        m.Reader(index_file_path="missing_index_file_path")
+    with pytest.raises(TypeError):
+        m.Reader(index_file_path=b"bytes-not-str")
+    with tempfile.TemporaryDirectory() as d:
+        w = m.Writer(index_file_path=os.path.join(d, "a.idx"), max_chunk_len=3)
+        with pytest.raises(ValueError, match="entry is too big"):
+            w.add_entry(text="abcd")
+        with pytest.raises(TypeError):
+            w.add_entry(text=b"ab")
+        with pytest.raises(FileNotFoundError):
+            w.add_entries_from_file_lines(input_file_path=os.path.join(d, "nope.txt"))
+
+
+def test_product_never_imports_oracle():
+    """The product path must not reference oracle/ (a CPU fallback would void parity)."""
+    pkg = os.path.join(ROOT, "pysubstringsearch_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if os.path.basename(dirpath) == "build":
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"(import|from|include|dlopen|CDLL)[^\n]*oracle", src), \
+                    "%s pulls in the oracle" % f
+    out = subprocess.run([sys.executable, "-c",
+                          "import sys, pysubstringsearch_b200; print(any(m.startswith('oracle') for m in sys.modules))"],
+                         cwd=ROOT, capture_output=True, text=True)
+    assert out.stdout.strip() == "False", out.stderr

@@ -1,0 +1,377 @@
+"""GPU parity tests (B200): the CUDA path, called through the C ABI (tests/capi.py) and the
+Python API, against the CPU oracle (oracle/) and the committed golden fixtures.
+Bit-exact everywhere: suffix arrays, index files, ordered result tuples."""
+import ctypes as C
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------------------------
+# radix sort
+# ------------------------------------------------------------------------------------
+def _radix_case(pss, n, begin, end, iota, seed, kind="random"):
+    import torch
+    rng = np.random.default_rng(seed)
+    if kind == "random":
+        keys = rng.integers(0, 2**63, size=n, dtype=np.uint64) * 2 + rng.integers(0, 2, size=n, dtype=np.uint64)
+    elif kind == "few":
+        keys = rng.integers(0, 3, size=n, dtype=np.uint64) << np.uint64(begin)
+    else:
+        keys = np.full(n, 0x0123456789ABCDEF, dtype=np.uint64)
+    vals = np.arange(n, dtype=np.uint32) if iota else rng.integers(0, 2**32, size=n, dtype=np.uint32)
+    dk = torch.from_numpy(keys.view(np.int64)).cuda()
+    dka = torch.empty_like(dk)
+    dv = torch.from_numpy(vals.view(np.int32)).cuda()
+    dva = torch.empty_like(dv)
+    torch.cuda.synchronize()
+    in_alt, npass = C.c_int32(0), C.c_int32(0)
+    pss.check(pss.lib.pss_radix_sort_pairs(dk.data_ptr(), dka.data_ptr(), 0 if iota else dv.data_ptr(), dva.data_ptr(),
+                                           n, begin, end, C.byref(in_alt), None, C.byref(npass), None))
+    torch.cuda.synchronize()
+    gk = (dka if in_alt.value else dk).cpu().numpy().view(np.uint64)
+    gv = (dva if (in_alt.value or iota) else dv).cpu().numpy().view(np.uint32)
+    width = end - begin
+    mask = np.uint64((1 << width) - 1) if width < 64 else np.uint64(0xFFFFFFFFFFFFFFFF)
+    order = np.argsort((keys >> np.uint64(begin)) & mask, kind="stable")
+    assert np.array_equal(gk, keys[order])
+    assert np.array_equal(gv, vals[order])
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 33, 4095, 4096, 4097, 100_000, (1 << 21) + 12345])
+def test_radix_sort_sizes(pss, n):
+    _radix_case(pss, n, 0, 64, False, n)
+
+
+def test_radix_sort_bit_ranges_and_skipped_digits(pss):
+    _radix_case(pss, 1 << 20, 0, 64, True, 1)
+    _radix_case(pss, 1 << 20, 5, 37, False, 2)
+    _radix_case(pss, 1 << 20, 0, 59, True, 3)
+    _radix_case(pss, 1 << 20, 8, 24, False, 4, kind="few")
+    _radix_case(pss, 1 << 20, 0, 64, True, 5, kind="const")     # every digit constant: zero passes
+    _radix_case(pss, 1 << 20, 0, 64, False, 6, kind="const")
+
+
+# ------------------------------------------------------------------------------------
+# suffix array
+# ------------------------------------------------------------------------------------
+def _text(kind, n, seed):
+    rng = np.random.default_rng(seed)
+    if kind == "words":
+        return synth.zipf_words_text(n, seed=seed, vocab=4096, block=1 << 16)
+    if kind == "bin":
+        return rng.integers(0, 256, size=n, dtype=np.uint8)
+    if kind == "tiny":
+        return rng.choice(np.array([0, 10, 97, 98, 255], dtype=np.uint8), size=n)
+    if kind == "acgt":
+        return synth.acgt_text(n, seed=seed, base_len=max(64, n // 9), mut_every=max(16, n // 7))
+    if kind == "same":
+        return np.full(n, 97, dtype=np.uint8)
+    if kind == "period":
+        t = np.tile(np.frombuffer(b"ACGT", dtype=np.uint8), n // 4 + 1)[:n].copy()
+        t[-1] = 10
+        return t
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["tiny", "words", "bin", "acgt", "same", "period"])
+def test_sa_matches_oracle(pss, oracle, kind):
+    for n in [1, 2, 3, 5, 17, 100, 1000, 4096, 4097, 65536, 300_000]:
+        if kind in ("same", "period") and n > 65536:
+            continue
+        t = _text(kind, n, n + 7)
+        assert np.array_equal(pss.libsais(t), oracle.suffix_array_port(t)), (kind, n)
+
+
+def test_sa_many_small_random(pss, oracle):
+    rng = np.random.default_rng(99)
+    for _ in range(150):
+        n = int(rng.integers(2, 400))
+        t = rng.choice(np.array([0, 10, 97, 98, 255], dtype=np.uint8), size=n)
+        assert np.array_equal(pss.libsais(t), oracle.suffix_array_bruteforce(t))
+
+
+def test_sa_golden_vectors(pss, vectors):
+    for v in vectors["sa"]:
+        t = bytes.fromhex(v["text"])
+        assert pss.libsais(t).tolist() == v["sa"]
+
+
+def test_sa_larger_vs_reference_libsais(pss, oracle):
+    """16 MiB config-1-like text and a 16 MiB repeat-heavy text against the reference's own
+    compiled libsais (oracle/_ref), else the port."""
+    ref = oracle.suffix_array_reference if oracle.reference_libsais_available() else oracle.suffix_array_port
+    for t in (synth.zipf_words_text(1 << 24, seed=5), synth.acgt_text(1 << 24, seed=6)):
+        assert np.array_equal(pss.libsais(t), ref(t))
+
+
+def test_libsais_freq_table(pss):
+    t = np.frombuffer(b"abracadabra\n", dtype=np.uint8)
+    sa = np.empty(len(t), dtype=np.int32)
+    freq = np.zeros(256, dtype=np.int32)
+    assert pss.lib.pss_libsais(t.ctypes.data, sa.ctypes.data, len(t), 0, freq.ctypes.data) == 0
+    assert freq[ord("a")] == 5 and freq[10] == 1 and freq.sum() == len(t)
+
+
+# ------------------------------------------------------------------------------------
+# Writer: index file byte-identical to the reference-equivalent writer
+# ------------------------------------------------------------------------------------
+def _write(cls, path, entries, mcl):
+    w = cls(path, mcl)
+    for e in entries:
+        w.add_entry(e)
+    w.finalize()
+    w.close()
+
+
+def test_writer_golden_containers(pss, vectors):
+    with tempfile.TemporaryDirectory() as d:
+        for case in vectors["containers"]:
+            p = os.path.join(d, "g.idx")
+            _write(pss.Writer, p, case["entries"], case["max_chunk_len"])
+            assert open(p, "rb").read().hex() == case["container_hex"]
+
+
+def test_writer_file_lines_golden(pss, vectors):
+    with tempfile.TemporaryDirectory() as d:
+        for case in vectors["file_lines"]:
+            src, p = os.path.join(d, "in.txt"), os.path.join(d, "g.idx")
+            open(src, "wb").write(bytes.fromhex(case["raw_hex"]))
+            w = pss.Writer(p)
+            assert w.add_entries_from_file_lines(src) == 0
+            assert w.finalize() == 0
+            w.close()
+            assert open(p, "rb").read().hex() == case["container_hex"]
+
+
+def test_writer_multichunk_vs_oracle(pss, oracle):
+    text = synth.zipf_words_text(3_000_000, seed=21, vocab=4096, block=1 << 16)
+    entries = bytes(text).split(b"\n")[:-1]
+    with tempfile.TemporaryDirectory() as d:
+        for mcl in (None, 1 << 20, 300_000, 4096):
+            a, b = os.path.join(d, "gpu.idx"), os.path.join(d, "cpu.idx")
+            _write(pss.Writer, a, entries, mcl)
+            _write(oracle.Writer, b, entries, mcl)
+            assert open(a, "rb").read() == open(b, "rb").read(), mcl
+        # file ingestion, same splitting rule, CRLF mixed in
+        src = os.path.join(d, "in.txt")
+        open(src, "wb").write(b"\r\n".join(entries[:5000]) + b"\n" + b"\n".join(entries[5000:20000]))
+        a, b = os.path.join(d, "gpu2.idx"), os.path.join(d, "cpu2.idx")
+        w = pss.Writer(a, 1 << 18)
+        assert w.add_entries_from_file_lines(src) == 0
+        w.close()
+        w = oracle.Writer(b, 1 << 18)
+        w.add_entries_from_file_lines(src)
+        w.close()
+        assert open(a, "rb").read() == open(b, "rb").read()
+
+
+def test_writer_capacity_quirks(pss, oracle):
+    """An entry that exactly fills the chunk doubles the capacity for good (Vec growth)."""
+    with tempfile.TemporaryDirectory() as d:
+        a, b = os.path.join(d, "a.idx"), os.path.join(d, "b.idx")
+        entries = ["1234", "x", "yy", "zzzz", "12345678", "q"]
+        for cls, p in ((pss.Writer, a), (oracle.Writer, b)):
+            w = cls(p, 4)
+            for e in entries:
+                try:
+                    rc = w.add_entry(e)
+                    assert rc in (0, None)
+                except ValueError:
+                    pass
+            w.close()
+        assert open(a, "rb").read() == open(b, "rb").read()
+
+
+# ------------------------------------------------------------------------------------
+# Reader: ordered result tuples identical to the oracle
+# ------------------------------------------------------------------------------------
+def _compare_searches(pss_reader, oracle_reader, patterns):
+    qo, ch, st, en, stats = pss_reader.search_batch(patterns)
+    counts, och, ost, oen = oracle_reader.search_multiple_tuples(patterns)
+    assert np.array_equal(np.diff(qo), counts)
+    assert np.array_equal(ch, och)
+    assert np.array_equal(st, ost)
+    assert np.array_equal(en, oen)
+    return stats
+
+
+def test_search_golden_containers(pss, vectors):
+    with tempfile.TemporaryDirectory() as d:
+        for case in vectors["containers"]:
+            p = os.path.join(d, "g.idx")
+            open(p, "wb").write(bytes.fromhex(case["container_hex"]))
+            r = pss.Reader(p)
+            for s in case["searches"]:
+                qo, ch, st, en, _ = r.search_batch([s["pattern"]])
+                assert (ch.tolist(), st.tolist(), en.tolist()) == (s["chunk"], s["start"], s["end"]), s["pattern"]
+            r.close()
+
+
+def test_search_random_patterns_vs_oracle(pss, oracle):
+    text = synth.zipf_words_text(4_000_000, seed=31, vocab=4096, block=1 << 16)
+    synth.plant(text, "google", 300, 1)
+    entries = bytes(text).split(b"\n")[:-1]
+    with tempfile.TemporaryDirectory() as d:
+        for mcl in (None, 1 << 20):
+            p = os.path.join(d, "s.idx")
+            _write(oracle.Writer, p, entries, mcl)      # reference-format file, read by the GPU reader
+            r, o = pss.Reader(p), oracle.Reader(p)
+            assert r.num_chunks == o.num_chunks
+            pats = synth.config2_queries(text, nq=600, seed=3)
+            pats += [b"", b"\n", b"e ", b"google", b"zzzzzz", b"a", b" ", b"\n\n", b"sojqmxwtxw",
+                     bytes(text[1000:1100]), bytes(text[5000:5070]), b"q" * 300]
+            stats = _compare_searches(r, o, pats)
+            assert stats["n_hits"] > len(text)          # the empty pattern alone matches every suffix
+            # one at a time == batched
+            for pat in pats[::50]:
+                _compare_searches(r, o, [pat])
+            r.close()
+            o.close()
+
+
+def test_search_binary_text_and_long_lines(pss, oracle):
+    rng = np.random.default_rng(8)
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "b.idx")
+        w = oracle.Writer(p, 1 << 16)
+        # few newlines → very long entries; 2-symbol alphabet → huge hit ranges
+        for _ in range(40):
+            w.add_entry(bytes(rng.choice(np.frombuffer(b"ab", dtype=np.uint8), size=int(rng.integers(1, 9000)))))
+        w.finalize()
+        w.close()
+        r, o = pss.Reader(p), oracle.Reader(p)
+        pats = [b"a", b"b", b"ab", b"ba", b"aaaa", b"abababab", b"", b"b\na", b"a" * 40, b"c"]
+        _compare_searches(r, o, pats)
+        r.close()
+        o.close()
+
+
+def test_empty_index_and_no_hits(pss, oracle):
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "e.idx")
+        w = pss.Writer(p)
+        assert w.finalize() == 0
+        w.close()
+        assert os.path.getsize(p) == 0
+        r = pss.Reader(p)
+        qo, ch, st, en, _ = r.search_batch(["a", ""])
+        assert qo.tolist() == [0, 0, 0] and len(ch) == 0
+        qo, ch, st, en, _ = r.search_batch([])
+        assert qo.tolist() == [0]
+        r.close()
+
+
+def test_sharded_readers_cover_the_index(pss, oracle):
+    text = synth.zipf_words_text(1_500_000, seed=41, vocab=2048, block=1 << 16)
+    entries = bytes(text).split(b"\n")[:-1]
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "m.idx")
+        _write(pss.Writer, p, entries, 1 << 18)
+        full = pss.Reader(p)
+        pats = synth.config2_queries(text, nq=100, seed=5) + [b"", b"e "]
+        qo, ch, st, en, _ = full.search_batch(pats)
+        parts = [pss.Reader(p, shard=(k, 3)) for k in range(3)]
+        rows = []
+        for k, part in enumerate(parts):
+            pqo, pch, pst, pen, _ = part.search_batch(pats)
+            assert all(c % 3 == k for c in pch)
+            q = np.repeat(np.arange(len(pats)), np.diff(pqo))
+            rows.append(np.stack([q, pch, np.arange(len(pch)), pst, pen], axis=1))
+        merged = np.concatenate(rows)
+        # (query, chunk) order; inside a pair the shard's own order is kept (stable)
+        merged = merged[np.lexsort((merged[:, 2], merged[:, 1], merged[:, 0]))]
+        assert np.array_equal(merged[:, 1], ch) and np.array_equal(merged[:, 3], st) and np.array_equal(merged[:, 4], en)
+        for part in parts:
+            part.close()
+        full.close()
+
+
+def test_device_resident_search_matches_host_api(pss):
+    import torch
+    text = synth.zipf_words_text(1_000_000, seed=51, vocab=2048, block=1 << 16)
+    entries = bytes(text).split(b"\n")[:-1]
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "m.idx")
+        _write(pss.Writer, p, entries, 1 << 19)
+        r = pss.Reader(p)
+        pats = synth.config2_queries(text, nq=200, seed=6)
+        qo, ch, st, en, _ = r.search_batch(pats)
+        blob, offs = synth.pack_patterns(pats)
+        d_blob = torch.from_numpy(blob).cuda()
+        d_offs = torch.from_numpy(offs).cuda()
+        cap = len(ch) + 10
+        out = [torch.empty(cap, dtype=torch.int32, device="cuda") for _ in range(4)]
+        n_entries, n_hits = C.c_int64(0), C.c_int64(0)
+        torch.cuda.synchronize()
+        rc = pss.lib.pss_reader_search_batch_device(r.h, d_blob.data_ptr(), d_offs.data_ptr(), len(pats), int(offs[-1]),
+                                                    out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                                    out[3].data_ptr(), cap, C.byref(n_entries), C.byref(n_hits), None)
+        assert rc == 0, pss.err()
+        k = n_entries.value
+        assert k == len(ch)
+        q = np.repeat(np.arange(len(pats)), np.diff(qo))
+        assert np.array_equal(out[0][:k].cpu().numpy(), q)
+        assert np.array_equal(out[1][:k].cpu().numpy(), ch)
+        assert np.array_equal(out[2][:k].cpu().numpy().view(np.uint32), st)
+        assert np.array_equal(out[3][:k].cpu().numpy().view(np.uint32), en)
+        # too-small buffers: reports the size needed, returns PSS_ERR_NOMEM
+        rc = pss.lib.pss_reader_search_batch_device(r.h, d_blob.data_ptr(), d_offs.data_ptr(), len(pats), int(offs[-1]),
+                                                    out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                                    out[3].data_ptr(), 3, C.byref(n_entries), C.byref(n_hits), None)
+        assert rc == -2 and n_entries.value == len(ch)
+        r.close()
+
+
+# ------------------------------------------------------------------------------------
+# Python API
+# ------------------------------------------------------------------------------------
+def test_python_api_reference_kats(kats):
+    """The reference's own test vectors through the drop-in import name."""
+    import pysubstringsearch
+    for k in kats:
+        if k["method"] == "open_missing":
+            with pytest.raises(FileNotFoundError):
+                pysubstringsearch.Reader(index_file_path=k["query"])
+            continue
+        with tempfile.TemporaryDirectory() as d:
+            p = f"{d}/output.idx"
+            w = pysubstringsearch.Writer(index_file_path=p)
+            for e in k["entries"]:
+                w.add_entry(text=e)
+            w.finalize()
+            r = pysubstringsearch.Reader(index_file_path=p)
+            got = r.search(substring=k["query"]) if k["method"] == "search" else r.search_multiple(substrings=k["query"])
+            assert sorted(got) == sorted(k["expected"]), k
+
+
+def test_python_api_ordered_vs_oracle(oracle, vectors):
+    import pysubstringsearch
+    with tempfile.TemporaryDirectory() as d:
+        for case in vectors["containers"]:
+            p = os.path.join(d, "g.idx")
+            w = pysubstringsearch.Writer(index_file_path=p, max_chunk_len=case["max_chunk_len"])
+            for e in case["entries"]:
+                w.add_entry(text=e)
+            w.finalize()
+            del w
+            r = pysubstringsearch.Reader(index_file_path=p)
+            for s in case["searches"]:
+                assert r.search(substring=s["pattern"]) == s["strings"]
+            assert r.search_multiple(substrings=[s["pattern"] for s in case["searches"]]) == case["search_multiple"]
+
+
+def test_python_writer_drop_flushes(oracle):
+    import pysubstringsearch
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "drop.idx")
+        w = pysubstringsearch.Writer(index_file_path=p)
+        w.add_entry(text="never finalized")
+        del w                                   # Drop → finalize (lib.rs:138-144)
+        assert oracle.Reader(p).search("final") == ["never finalized"]
