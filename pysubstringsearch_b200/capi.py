@@ -1,11 +1,12 @@
-"""ctypes binding of include/pss.h used by the tests (and mirrored in INTEGRATION.md)."""
+"""ctypes binding of include/pss.h (libpss_b200.so): the plain C ABI, for callers that want
+result tuples / device-resident entry points instead of the Writer/Reader classes.  Used by
+bench.py and the tests; mirrored by the stubs in INTEGRATION.md.  No compute happens here."""
 import ctypes as C
 import os
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(ROOT, "pysubstringsearch_b200", "libpss_b200.so")
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpss_b200.so")
 lib = C.CDLL(LIB_PATH)
 
 vp, i32, i64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t

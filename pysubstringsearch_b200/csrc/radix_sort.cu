@@ -13,7 +13,7 @@ constexpr uint32_t FLAG_EMPTY = 0u;
 constexpr uint32_t FLAG_LOCAL = 1u;  // value = this tile's count
 constexpr uint32_t FLAG_INCL  = 2u;  // value = inclusive prefix over tiles 0..t
 constexpr uint32_t FLAG_ABORT = 3u;  // a predecessor gave up (watchdog)
-constexpr uint32_t SPIN_LIMIT = 1u << 24;
+constexpr uint32_t SPIN_LIMIT = 1u << 22;
 
 constexpr int CTRL_TICKET  = 0;   // [0..8)
 constexpr int CTRL_ERROR   = 8;
@@ -106,10 +106,12 @@ radix_scan_kernel(const uint32_t *__restrict__ g_hist, uint32_t *__restrict__ bi
 // ------------------------------------------------------------------------------------
 // One digit pass.
 // ------------------------------------------------------------------------------------
+template <int THREADS, int IPT>
 struct PassSmem {
-    uint64_t keys[PASS_TILE];
-    uint32_t vals[PASS_TILE];
-    uint32_t warp_hist[PASS_THREADS / 32][RADIX];
+    static constexpr int TILE = THREADS * IPT;
+    uint64_t keys[TILE];
+    uint32_t vals[TILE];
+    uint32_t warp_hist[THREADS / 32][RADIX];
     uint32_t bin_start[RADIX];   // exclusive scan over digits of the tile's counts
     uint32_t glob_off[RADIX];    // global offset of the digit's run minus bin_start (mod 2^32)
     uint32_t scan_warp[RADIX / 32];
@@ -117,18 +119,23 @@ struct PassSmem {
     uint32_t abort;
 };
 
-template <bool IOTA_VALS>
-__global__ void __launch_bounds__(PASS_THREADS, 2)
+// tile_state[tile][digit]: bits 31..30 = FLAG_*, bits 29..0 = count (LOCAL) or inclusive
+// prefix over tiles 0..tile (INCL).  One word carries flag and value, so no fence is needed.
+template <int THREADS, int IPT, int MIN_BLOCKS, bool IOTA_VALS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out,
                      const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out,
                      uint32_t n, int shift, uint32_t digit_mask,
                      const uint32_t *__restrict__ bin_base, uint32_t *tile_state,
                      uint32_t *ctrl, int pass_slot) {
+    static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is needed");
+    using Smem = PassSmem<THREADS, IPT>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    PassSmem &s = *reinterpret_cast<PassSmem *>(smem_raw);
+    Smem &s = *reinterpret_cast<Smem *>(smem_raw);
 
-    constexpr int WARPS      = PASS_THREADS / 32;
-    constexpr int WARP_ITEMS = 32 * PASS_IPT;
+    constexpr int TILE       = THREADS * IPT;
+    constexpr int WARPS      = THREADS / 32;
+    constexpr int WARP_ITEMS = 32 * IPT;
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
 
     // Tiles are handed out in launch order so that every predecessor of a running tile
@@ -142,22 +149,22 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict_
     for (int i = 0; i < RADIX / 32; ++i) s.warp_hist[warp][i * 32 + lane] = 0;
     __syncthreads();
     const uint32_t tile      = s.tile;
-    const uint32_t tile_base = tile * PASS_TILE;
+    const uint32_t tile_base = tile * TILE;
     const uint32_t warp_base = tile_base + warp * WARP_ITEMS;
-    const uint32_t valid     = min((uint32_t)PASS_TILE, n - tile_base);
+    const uint32_t valid     = min((uint32_t)TILE, n - tile_base);
 
     // ---- load (warp-striped: item j of lane l sits at warp_base + j*32 + l) ----------
-    uint64_t key[PASS_IPT];
-    uint32_t val[PASS_IPT];
-    if (valid == PASS_TILE) {
+    uint64_t key[IPT];
+    uint32_t val[IPT];
+    if (valid == TILE) {
 #pragma unroll
-        for (int j = 0; j < PASS_IPT; ++j) key[j] = ld_stream_u64(keys_in + warp_base + j * 32 + lane);
+        for (int j = 0; j < IPT; ++j) key[j] = ld_stream_u64(keys_in + warp_base + j * 32 + lane);
 #pragma unroll
-        for (int j = 0; j < PASS_IPT; ++j)
+        for (int j = 0; j < IPT; ++j)
             val[j] = IOTA_VALS ? (warp_base + j * 32 + lane) : ld_stream_u32(vals_in + warp_base + j * 32 + lane);
     } else {
 #pragma unroll
-        for (int j = 0; j < PASS_IPT; ++j) {
+        for (int j = 0; j < IPT; ++j) {
             uint32_t i = warp_base + j * 32 + lane;
             bool ok = i < n;
             key[j] = ok ? ld_stream_u64(keys_in + i) : ~0ull;
@@ -165,29 +172,18 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict_
         }
     }
 
-    // ---- rank inside the warp: match_any groups equal digits, the group's lowest lane
-    //      bumps the warp's private counter, everyone derives a stable rank ------------
-    uint16_t rank[PASS_IPT];
+    // ---- early counts: warp-private digit histogram, so the tile's counts can be
+    //      published (and the look-back started) before the expensive ranking -----------
     uint32_t *wh = s.warp_hist[warp];
-    const uint32_t lt = lanemask_lt();
 #pragma unroll
-    for (int j = 0; j < PASS_IPT; ++j) {
-        uint32_t d     = (uint32_t)(key[j] >> shift) & digit_mask;
-        uint32_t peers = __match_any_sync(0xffffffffu, d);
-        int leader     = __ffs(peers) - 1;
-        uint32_t old   = 0;
-        if ((int)lane == leader) {
-            old   = wh[d];
-            wh[d] = old + __popc(peers);
-        }
-        old     = __shfl_sync(0xffffffffu, old, leader);
-        rank[j] = (uint16_t)(old + __popc(peers & lt));
-        __syncwarp();
-    }
+    for (int j = 0; j < IPT; ++j) atomicAdd(&wh[(uint32_t)(key[j] >> shift) & digit_mask], 1u);
     __syncthreads();
 
-    // ---- per digit: prefix over warps, publish the tile count, scan over digits -------
+    // ---- per digit (threads 0..255): offsets of each warp inside the digit's bin, publish
+    //      the tile count, put the first look-back loads in flight, scan over digits -------
+    constexpr int LB = 4;
     uint32_t count = 0;
+    uint32_t lbv[LB];
     if (tid < RADIX) {
         uint32_t run = 0;
 #pragma unroll
@@ -199,6 +195,11 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict_
         count = run;
         st_volatile_u32(tile_state + (size_t)tile * RADIX + tid,
                         ((tile == 0 ? FLAG_INCL : FLAG_LOCAL) << FLAG_SHIFT) | count);
+#pragma unroll
+        for (int j = 0; j < LB; ++j) {
+            const int64_t q = (int64_t)tile - 1 - j;
+            lbv[j] = q >= 0 ? ld_volatile_u32(tile_state + (size_t)q * RADIX + tid) : (FLAG_INCL << FLAG_SHIFT);
+        }
         uint32_t incl = count;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -206,31 +207,70 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict_
             if (lane >= (uint32_t)o) incl += y;
         }
         if (lane == 31) s.scan_warp[warp] = incl;
-        s.bin_start[tid] = incl - count;  // warp-local exclusive; fixed up below
-    }
-    __syncthreads();
-    if (tid < RADIX) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 digit warps only
         uint32_t add = 0;
         for (uint32_t w = 0; w < warp; ++w) add += s.scan_warp[w];
-        uint32_t bstart  = s.bin_start[tid] + add;
-        s.bin_start[tid] = bstart;
+        s.bin_start[tid] = incl - count + add;
+    }
+    __syncthreads();
 
-        // ---- decoupled look-back: one thread per digit walks the preceding tiles -----
+    // ---- rank and stage: match_any groups equal digits inside the warp; the group's lowest
+    //      lane advances the warp's running offset; records go to shared memory in digit order
+    const uint32_t lt = lanemask_lt();
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+        const uint32_t d     = (uint32_t)(key[j] >> shift) & digit_mask;
+        const uint32_t bs    = s.bin_start[d];
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const int leader     = __ffs(peers) - 1;
+        uint32_t old         = 0;
+        if ((int)lane == leader) {
+            old   = wh[d];
+            wh[d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        const uint32_t pos = bs + old + __popc(peers & lt);
+        s.keys[pos] = key[j];
+        s.vals[pos] = val[j];
+        __syncwarp();
+    }
+
+    // ---- decoupled look-back (digit threads): the first LB predecessor states were loaded
+    //      before the ranking; keep walking LB at a time until an inclusive prefix is met.
+    //      (Measured on B200: wider batches, an early spin before the ranking, and a
+    //      status-word protocol with fences were all slower than this.) -------------------
+    if (tid < RADIX) {
         uint32_t excl = 0;
         bool aborted  = false;
         if (tile > 0) {
-            int64_t p = (int64_t)tile - 1;
+            int64_t p      = (int64_t)tile - 1;
+            uint32_t spins = 0;
+            bool done      = false;
             while (true) {
-                const uint32_t *slot = tile_state + (size_t)p * RADIX + tid;
-                uint32_t v, spins = 0;
-                do {
-                    v = ld_volatile_u32(slot);
-                } while ((v >> FLAG_SHIFT) == FLAG_EMPTY && ++spins < SPIN_LIMIT);
-                uint32_t f = v >> FLAG_SHIFT;
-                if (f == FLAG_EMPTY || f == FLAG_ABORT) { aborted = true; break; }
-                excl += v & VALUE_MASK;
-                if (f == FLAG_INCL) break;
-                --p;
+                int consumed = 0;
+                bool stopped = false;
+#pragma unroll
+                for (int j = 0; j < LB; ++j) {
+                    const uint32_t f = lbv[j] >> FLAG_SHIFT;
+                    if (done || stopped) continue;
+                    if (f == FLAG_EMPTY) {
+                        stopped = true;            // predecessor not published yet: poll it again
+                    } else if (f == FLAG_ABORT) {
+                        aborted = done = true;
+                    } else {
+                        excl += lbv[j] & VALUE_MASK;
+                        ++consumed;
+                        if (f == FLAG_INCL) done = true;
+                    }
+                }
+                p -= consumed;
+                if (stopped && consumed == 0 && ++spins >= SPIN_LIMIT) aborted = done = true;
+                if (done) break;
+#pragma unroll
+                for (int j = 0; j < LB; ++j) {
+                    const int64_t q = p - j;
+                    lbv[j] = q >= 0 ? ld_volatile_u32(tile_state + (size_t)q * RADIX + tid) : (FLAG_INCL << FLAG_SHIFT);
+                }
             }
             if (aborted) {
                 st_volatile_u32(tile_state + (size_t)tile * RADIX + tid, FLAG_ABORT << FLAG_SHIFT);
@@ -241,25 +281,15 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict_
                                 (FLAG_INCL << FLAG_SHIFT) | (excl + count));
             }
         }
-        s.glob_off[tid] = bin_base[tid] + excl - bstart;
+        s.glob_off[tid] = bin_base[tid] + excl - s.bin_start[tid];
     }
     __syncthreads();
     if (s.abort) return;
 
-    // ---- stage the tile in shared memory in digit order ------------------------------
-#pragma unroll
-    for (int j = 0; j < PASS_IPT; ++j) {
-        uint32_t d   = (uint32_t)(key[j] >> shift) & digit_mask;
-        uint32_t pos = s.bin_start[d] + wh[d] + rank[j];
-        s.keys[pos]  = key[j];
-        s.vals[pos]  = val[j];
-    }
-    __syncthreads();
-
     // ---- coalesced per-digit runs to global memory ------------------------------------
 #pragma unroll
-    for (int j = 0; j < PASS_IPT; ++j) {
-        uint32_t i = j * PASS_THREADS + tid;
+    for (int j = 0; j < IPT; ++j) {
+        uint32_t i = j * THREADS + tid;
         if (i < valid) {
             uint64_t k   = s.keys[i];
             uint32_t d   = (uint32_t)(k >> shift) & digit_mask;
@@ -271,6 +301,24 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict_
         }
     }
 }
+
+// Tile geometries compiled in; PSS_PASS_CFG selects one (default 0).
+struct PassConfig {
+    int threads, ipt, smem;
+    const void *fn_iota, *fn_vals;
+};
+#define PSS_PASS_CONFIG(T, I, B)                                                             \
+    {T, I, (int)sizeof(PassSmem<T, I>), (const void *)onesweep_pass_kernel<T, I, B, true>,    \
+     (const void *)onesweep_pass_kernel<T, I, B, false>}
+const PassConfig kPassConfigs[] = {
+    PSS_PASS_CONFIG(256, 16, 3),   // 0 (default): 4096-record tiles, 3 CTAs/SM, 16 records in flight per thread
+    PSS_PASS_CONFIG(512, 8, 2),    // 1: 4096-record tiles, 2 CTAs/SM
+    PSS_PASS_CONFIG(512, 12, 2),   // 2: 6144-record tiles, 2 CTAs/SM
+    PSS_PASS_CONFIG(384, 16, 2),   // 3: 6144-record tiles, 2 CTAs/SM
+    PSS_PASS_CONFIG(256, 12, 4),   // 4: 3072-record tiles, 4 CTAs/SM
+    PSS_PASS_CONFIG(256, 24, 2),   // 5: 6144-record tiles, 2 CTAs/SM
+};
+constexpr int kNumPassConfigs = (int)(sizeof(kPassConfigs) / sizeof(kPassConfigs[0]));
 
 __global__ void iota_kernel(uint32_t *v, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -293,15 +341,20 @@ int RadixSorter::init(int device) {
     PSS_CUDA_TRY(cudaMallocHost(&h_ctrl_, CTRL_WORDS * sizeof(uint32_t)));
     for (auto &e : ev_) PSS_CUDA_TRY(cudaEventCreate(&e));
     ev_ready_ = true;
-    PSS_CUDA_TRY(cudaFuncSetAttribute(onesweep_pass_kernel<true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)));
-    PSS_CUDA_TRY(cudaFuncSetAttribute(onesweep_pass_kernel<false>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)));
+    cfg_ = 0;
+    if (const char *e = std::getenv("PSS_PASS_CFG")) {
+        int v = std::atoi(e);
+        if (v >= 0 && v < kNumPassConfigs) cfg_ = v;
+    }
+    const PassConfig &pc = kPassConfigs[cfg_];
+    tile_items_ = pc.threads * pc.ipt;
+    PSS_CUDA_TRY(cudaFuncSetAttribute(pc.fn_iota, cudaFuncAttributeMaxDynamicSharedMemorySize, pc.smem));
+    PSS_CUDA_TRY(cudaFuncSetAttribute(pc.fn_vals, cudaFuncAttributeMaxDynamicSharedMemorySize, pc.smem));
     return PSS_OK;
 }
 
 int RadixSorter::ensure(int64_t n) {
-    int64_t tiles = div_up(n, PASS_TILE);
+    int64_t tiles = div_up(n, tile_items_);
     if (tiles < 1) tiles = 1;
     if (tiles <= tile_capacity_) return PSS_OK;
     PSS_CUDA_TRY(cudaSetDevice(device_));
@@ -344,7 +397,8 @@ int RadixSorter::sort(uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, uint32
 
     const int last_bits      = (end_bit - begin_bit) - (npass - 1) * RADIX_BITS;
     const uint32_t last_mask = (1u << last_bits) - 1u;
-    const uint32_t tiles     = (uint32_t)div_up(n, PASS_TILE);
+    const uint32_t tiles     = (uint32_t)div_up(n, tile_items_);
+    const PassConfig &pc     = kPassConfigs[cfg_];
 
     PSS_CUDA_TRY(cudaMemsetAsync(d_hist_, 0, MAX_PASSES * RADIX * sizeof(uint32_t), stream));
     PSS_CUDA_TRY(cudaMemsetAsync(d_ctrl_, 0, CTRL_WORDS * sizeof(uint32_t), stream));
@@ -371,12 +425,15 @@ int RadixSorter::sort(uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, uint32
         const uint32_t mask = (p == npass - 1) ? last_mask : (uint32_t)(RADIX - 1);
         PSS_CUDA_TRY(cudaMemsetAsync(d_tile_state_, 0, (size_t)tiles * RADIX * sizeof(uint32_t), stream));
         if (timed) PSS_CUDA_TRY(cudaEventRecord(ev_[2 * executed], stream));
-        if (iota) {
-            onesweep_pass_kernel<true><<<tiles, PASS_THREADS, sizeof(PassSmem), stream>>>(
-                kin, kout, nullptr, vout, n, shift, mask, d_bin_base_ + p * RADIX, d_tile_state_, d_ctrl_, p);
-        } else {
-            onesweep_pass_kernel<false><<<tiles, PASS_THREADS, sizeof(PassSmem), stream>>>(
-                kin, kout, vin, vout, n, shift, mask, d_bin_base_ + p * RADIX, d_tile_state_, d_ctrl_, p);
+        {
+            const uint32_t *vals_arg = iota ? nullptr : vin;
+            const uint32_t *base_arg = d_bin_base_ + p * RADIX;
+            uint32_t n_arg = n, mask_arg = mask;
+            int shift_arg = shift, slot_arg = p;
+            void *args[] = {&kin, &kout, &vals_arg, &vout, &n_arg, &shift_arg, &mask_arg, &base_arg,
+                            &d_tile_state_, &d_ctrl_, &slot_arg};
+            PSS_CUDA_TRY(cudaLaunchKernel(iota ? pc.fn_iota : pc.fn_vals, dim3(tiles), dim3(pc.threads), args,
+                                          (size_t)pc.smem, stream));
         }
         PSS_LAUNCH_CHECK();
         if (timed) PSS_CUDA_TRY(cudaEventRecord(ev_[2 * executed + 1], stream));

@@ -20,10 +20,6 @@ constexpr int RADIX_BITS = 8;
 constexpr int RADIX      = 1 << RADIX_BITS;
 constexpr int MAX_PASSES = 8;
 
-// Tile geometry of the pass kernel (tuned on B200).
-constexpr int PASS_THREADS = 512;
-constexpr int PASS_IPT     = 8;
-constexpr int PASS_TILE    = PASS_THREADS * PASS_IPT;
 
 struct SortProfile {
     bool  timed    = false;  // in: record CUDA events around the histogram and every pass
@@ -58,6 +54,8 @@ public:
 private:
     int       device_        = -1;
     int       num_sms_       = 0;
+    int       cfg_           = 0;     // index into the compiled tile geometries (PSS_PASS_CFG)
+    int       tile_items_    = 4096;  // records per tile of the selected geometry
     int64_t   tile_capacity_ = 0;
     uint32_t *d_hist_        = nullptr;  // [MAX_PASSES][RADIX]
     uint32_t *d_bin_base_    = nullptr;  // [MAX_PASSES][RADIX]

@@ -329,6 +329,13 @@ int SaBuilder::init(int device, int64_t max_n) {
     if (device >= ndev) return fail(PSS_ERR_ARG, "device index out of range");
     PSS_CUDA_TRY(cudaSetDevice(device));
     device_ = device;
+    // The rank gather / scatter of prefix doubling touches 4 bytes per random sector: ask
+    // L2 not to pull in neighbouring sectors on those misses (a hint; ignored if unsupported).
+    if (const char *e = std::getenv("PSS_L2_FETCH")) {
+        int g = std::atoi(e);
+        if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);
+        cudaGetLastError();
+    }
     PSS_CUDA_TRY(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     PSS_CUDA_TRY(cudaEventCreate(&ev_begin_));
     PSS_CUDA_TRY(cudaEventCreate(&ev_end_));

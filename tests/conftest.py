@@ -65,5 +65,5 @@ def oracle():
 
 @pytest.fixture(scope="session")
 def pss():
-    from tests import capi
+    from pysubstringsearch_b200 import capi
     return capi
