@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -42,6 +43,47 @@ struct Pinned {
         PSS_CUDA_TRY(cudaMallocHost(&p, n));
         cap = n;
         return PSS_OK;
+    }
+};
+
+// Pool of pinned host blocks that back pss_result arrays: the device→host copy of a batch
+// lands directly in the memory the caller reads, and the blocks are recycled across batches
+// (pinning a fresh block per batch costs more than the whole search).
+struct PinnedBlock {
+    void  *p   = nullptr;
+    size_t cap = 0;
+};
+struct PinnedPool {
+    std::mutex mu;
+    std::vector<PinnedBlock> free_;
+    ~PinnedPool() {
+        for (auto &b : free_) cudaFreeHost(b.p);
+    }
+    int acquire(size_t bytes, PinnedBlock *out) {
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            size_t best = free_.size();
+            for (size_t i = 0; i < free_.size(); ++i)
+                if (free_[i].cap >= bytes && (best == free_.size() || free_[i].cap < free_[best].cap)) best = i;
+            if (best != free_.size()) {
+                *out = free_[best];
+                free_.erase(free_.begin() + best);
+                return PSS_OK;
+            }
+        }
+        size_t cap = 1 << 16;
+        while (cap < bytes) cap *= 2;
+        PinnedBlock b;
+        PSS_CUDA_TRY(cudaMallocHost(&b.p, cap));
+        b.cap = cap;
+        *out  = b;
+        return PSS_OK;
+    }
+    void release(PinnedBlock b) {
+        if (!b.p) return;
+        std::lock_guard<std::mutex> lock(mu);
+        if (free_.size() < 4) free_.push_back(b);
+        else cudaFreeHost(b.p);
     }
 };
 
@@ -206,10 +248,40 @@ struct ChunkHost {
     int32_t *d_sa   = nullptr;
 };
 
-// Collects the entries of every sub-batch into host vectors.
+// One batch of results in a pinned block: [chunk i32 x cap][start u32 x cap][end u32 x cap].
+struct ResultOwner {
+    pss_result pub;
+    std::vector<int64_t> query_offsets;
+    std::shared_ptr<PinnedPool> pool;
+    PinnedBlock blk;
+    int64_t cap = 0, used = 0;
+    ~ResultOwner() { if (pool) pool->release(blk); }
+    int32_t  *chunk() const { return static_cast<int32_t *>(blk.p); }
+    uint32_t *start() const { return reinterpret_cast<uint32_t *>(chunk() + cap); }
+    uint32_t *end() const { return start() + cap; }
+    int ensure(int64_t need) {
+        if (need <= cap) return PSS_OK;
+        int64_t ncap = std::max<int64_t>(need + need / 2, 1 << 12);
+        PinnedBlock nb;
+        PSS_TRY(pool->acquire((size_t)ncap * 12, &nb));
+        ncap = (int64_t)(nb.cap / 12);
+        if (used) {
+            int32_t *nc = static_cast<int32_t *>(nb.p);
+            std::memcpy(nc, chunk(), (size_t)used * 4);
+            std::memcpy(nc + ncap, start(), (size_t)used * 4);
+            std::memcpy(nc + 2 * ncap, end(), (size_t)used * 4);
+        }
+        pool->release(blk);
+        blk = nb;
+        cap = ncap;
+        return PSS_OK;
+    }
+};
+
+// Sends the entries of every sub-batch to the result being built.  Lives in the reader:
+// its device staging buffers are allocated once and only grow.
 struct HostSink : SearchSink {
-    std::vector<int32_t>  chunk;
-    std::vector<uint32_t> start, end;
+    ResultOwner *res = nullptr;
     int32_t  *d_chunk = nullptr;
     uint32_t *d_start = nullptr, *d_end = nullptr;
     int64_t   cap = 0;
@@ -218,7 +290,7 @@ struct HostSink : SearchSink {
         if (count > cap) {
             cudaFree(d_chunk); cudaFree(d_start); cudaFree(d_end);
             d_chunk = nullptr; d_start = d_end = nullptr; cap = 0;
-            int64_t nc = std::max<int64_t>(count + count / 4, 1 << 12);
+            int64_t nc = std::max<int64_t>(count + count / 2, 1 << 16);
             PSS_CUDA_TRY(cudaMalloc(&d_chunk, nc * sizeof(int32_t)));
             PSS_CUDA_TRY(cudaMalloc(&d_start, nc * sizeof(uint32_t)));
             PSS_CUDA_TRY(cudaMalloc(&d_end, nc * sizeof(uint32_t)));
@@ -229,11 +301,12 @@ struct HostSink : SearchSink {
     }
     int commit(int64_t count, cudaStream_t st) override {
         if (count == 0) return PSS_OK;
-        const size_t at = chunk.size();
-        chunk.resize(at + count); start.resize(at + count); end.resize(at + count);
-        PSS_CUDA_TRY(cudaMemcpyAsync(chunk.data() + at, d_chunk, count * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        PSS_CUDA_TRY(cudaMemcpyAsync(start.data() + at, d_start, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        PSS_CUDA_TRY(cudaMemcpyAsync(end.data() + at, d_end, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        PSS_TRY(res->ensure(res->used + count));
+        const int64_t at = res->used;
+        PSS_CUDA_TRY(cudaMemcpyAsync(res->chunk() + at, d_chunk, count * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        PSS_CUDA_TRY(cudaMemcpyAsync(res->start() + at, d_start, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        PSS_CUDA_TRY(cudaMemcpyAsync(res->end() + at, d_end, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        res->used += count;
         return PSS_OK;
     }
 };
@@ -289,6 +362,9 @@ struct pss_reader {
     int64_t *d_off = nullptr;
     size_t   d_pat_cap = 0, d_off_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    HostSink sink;
+    std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
+    std::vector<int64_t> per_pair;
 
     ~pss_reader() {
         if (searcher.device() >= 0) cudaSetDevice(searcher.device());
@@ -391,13 +467,6 @@ static int reader_open(const char *path, int shard_rank, int shard_count, pss_re
     return PSS_OK;
 }
 
-struct ResultOwner {
-    pss_result pub;
-    std::vector<int64_t>  query_offsets;
-    std::vector<int32_t>  chunk;
-    std::vector<uint32_t> start, end;
-};
-
 extern "C" {
 
 int32_t pss_reader_open(const char *index_file_path, pss_reader **out) {
@@ -433,6 +502,7 @@ int32_t pss_reader_search_batch(pss_reader *r, const uint8_t *patterns, const in
     if (!res) return fail(PSS_ERR_NOMEM, "out of host memory");
     std::memset(&res->pub, 0, sizeof(res->pub));
     res->query_offsets.assign((size_t)nq + 1, 0);
+    res->pool = r->pool;
     const int nc = r->searcher.num_chunks();
     if (nq > 0 && nc > 0) {
         const int64_t total = offsets[nq];
@@ -461,11 +531,14 @@ int32_t pss_reader_search_batch(pss_reader *r, const uint8_t *patterns, const in
         if (total)
             PSS_CUDA_TRY(cudaMemcpyAsync(r->d_pat, static_cast<uint8_t *>(r->h_pat.p) + off_bytes, (size_t)total,
                                          cudaMemcpyHostToDevice, s));
-        HostSink sink;
-        std::vector<int64_t> per_pair((size_t)nq * nc, 0);
+        r->sink.res = res.get();
+        std::vector<int64_t> &per_pair = r->per_pair;
+        per_pair.assign((size_t)nq * nc, 0);
         SearchTimes times;
         int64_t n_hits = 0;
-        PSS_TRY(r->searcher.search(r->d_pat, r->d_off, nq, s, &sink, per_pair.data(), &n_hits, &times));
+        int rc = r->searcher.search(r->d_pat, r->d_off, nq, s, &r->sink, per_pair.data(), &n_hits, &times);
+        r->sink.res = nullptr;
+        if (rc != PSS_OK) return rc;
         PSS_CUDA_TRY(cudaEventRecord(r->ev1, s));
         PSS_CUDA_TRY(cudaEventSynchronize(r->ev1));
         PSS_CUDA_TRY(cudaEventElapsedTime(&times.ms_total, r->ev0, r->ev1));
@@ -474,10 +547,7 @@ int32_t pss_reader_search_batch(pss_reader *r, const uint8_t *patterns, const in
             for (int c = 0; c < nc; ++c) cnt += per_pair[(size_t)q * nc + c];
             res->query_offsets[q + 1] = res->query_offsets[q] + cnt;
         }
-        res->chunk.swap(sink.chunk);
-        res->start.swap(sink.start);
-        res->end.swap(sink.end);
-        if ((int64_t)res->chunk.size() != res->query_offsets[nq])
+        if (res->used != res->query_offsets[nq])
             return fail(PSS_ERR_CUDA, "internal error: per-query counts do not add up to the entry count");
         res->pub.n_hits     = n_hits;
         res->pub.ms_bounds  = times.ms_bounds;
@@ -486,11 +556,11 @@ int32_t pss_reader_search_batch(pss_reader *r, const uint8_t *patterns, const in
         res->pub.ms_total   = times.ms_total;
     }
     res->pub.n_queries     = nq;
-    res->pub.n_entries     = (int64_t)res->chunk.size();
+    res->pub.n_entries     = res->used;
     res->pub.query_offsets = res->query_offsets.data();
-    res->pub.chunk_id      = res->chunk.data();
-    res->pub.line_start    = res->start.data();
-    res->pub.line_end      = res->end.data();
+    res->pub.chunk_id      = res->used ? res->chunk() : nullptr;
+    res->pub.line_start    = res->used ? res->start() : nullptr;
+    res->pub.line_end      = res->used ? res->end() : nullptr;
     *out = &res.release()->pub;
     return PSS_OK;
 }

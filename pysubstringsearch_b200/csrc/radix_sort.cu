@@ -121,7 +121,9 @@ struct PassSmem {
 
 // tile_state[tile][digit]: bits 31..30 = FLAG_*, bits 29..0 = count (LOCAL) or inclusive
 // prefix over tiles 0..tile (INCL).  One word carries flag and value, so no fence is needed.
-template <int THREADS, int IPT, int MIN_BLOCKS, bool IOTA_VALS>
+// MODE: 0 = (key, value) records, 1 = values are 0..n-1 (generated, not loaded),
+//       2 = keys only (used to partition (index, rank) pairs before the rank scatter).
+template <int THREADS, int IPT, int MIN_BLOCKS, int MODE>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out,
                      const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out,
@@ -154,21 +156,25 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict_
     const uint32_t valid     = min((uint32_t)TILE, n - tile_base);
 
     // ---- load (warp-striped: item j of lane l sits at warp_base + j*32 + l) ----------
+    constexpr bool IOTA_VALS = (MODE == 1);
+    constexpr bool HAS_VALS  = (MODE != 2);
     uint64_t key[IPT];
-    uint32_t val[IPT];
+    uint32_t val[HAS_VALS ? IPT : 1];
     if (valid == TILE) {
 #pragma unroll
         for (int j = 0; j < IPT; ++j) key[j] = ld_stream_u64(keys_in + warp_base + j * 32 + lane);
+        if (HAS_VALS) {
 #pragma unroll
-        for (int j = 0; j < IPT; ++j)
-            val[j] = IOTA_VALS ? (warp_base + j * 32 + lane) : ld_stream_u32(vals_in + warp_base + j * 32 + lane);
+            for (int j = 0; j < IPT; ++j)
+                val[j] = IOTA_VALS ? (warp_base + j * 32 + lane) : ld_stream_u32(vals_in + warp_base + j * 32 + lane);
+        }
     } else {
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
             uint32_t i = warp_base + j * 32 + lane;
             bool ok = i < n;
             key[j] = ok ? ld_stream_u64(keys_in + i) : ~0ull;
-            val[j] = ok ? (IOTA_VALS ? i : ld_stream_u32(vals_in + i)) : 0u;
+            if (HAS_VALS) val[j] = ok ? (IOTA_VALS ? i : ld_stream_u32(vals_in + i)) : 0u;
         }
     }
 
@@ -214,6 +220,45 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict_
     }
     __syncthreads();
 
+    // ---- decoupled look-back state machine (digit threads).  lb_consume() folds the LB
+    //      predecessor states loaded last into `excl` (in order, stopping at an inclusive
+    //      prefix or at a predecessor that has not published yet); lb_issue() puts the next
+    //      LB loads in flight.  The steps are interleaved with the ranking loop below, so the
+    //      L2 round trips of the walk overlap with the ranking instead of following it. -----
+    uint32_t excl     = 0;
+    int64_t  lb_p     = (int64_t)tile - 1;
+    bool     lb_done  = (tile == 0) || (tid >= RADIX);
+    bool     lb_abort = false;
+    bool     lb_progress = false;
+    auto lb_consume = [&]() {
+        int consumed = 0;
+        bool stopped = false;
+#pragma unroll
+        for (int j = 0; j < LB; ++j) {
+            const uint32_t f = lbv[j] >> FLAG_SHIFT;
+            if (lb_done || stopped) continue;
+            if (f == FLAG_EMPTY) {
+                stopped = true;                    // predecessor not published yet: poll it again
+            } else if (f == FLAG_ABORT) {
+                lb_abort = lb_done = true;
+            } else {
+                excl += lbv[j] & VALUE_MASK;
+                ++consumed;
+                if (f == FLAG_INCL) lb_done = true;
+            }
+        }
+        lb_p -= consumed;
+        lb_progress = consumed > 0;
+    };
+    auto lb_issue = [&]() {
+        if (lb_done) return;
+#pragma unroll
+        for (int j = 0; j < LB; ++j) {
+            const int64_t q = lb_p - j;
+            lbv[j] = q >= 0 ? ld_volatile_u32(tile_state + (size_t)q * RADIX + tid) : (FLAG_INCL << FLAG_SHIFT);
+        }
+    };
+
     // ---- rank and stage: match_any groups equal digits inside the warp; the group's lowest
     //      lane advances the warp's running offset; records go to shared memory in digit order
     const uint32_t lt = lanemask_lt();
@@ -231,47 +276,25 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict_
         old = __shfl_sync(0xffffffffu, old, leader);
         const uint32_t pos = bs + old + __popc(peers & lt);
         s.keys[pos] = key[j];
-        s.vals[pos] = val[j];
+        if (HAS_VALS) s.vals[pos] = val[j];
         __syncwarp();
+        if ((j & 3) == 3 && j + 1 < IPT && !lb_done) {   // warp-divergent only in the digit warps' walk
+            lb_consume();
+            lb_issue();
+        }
     }
 
-    // ---- decoupled look-back (digit threads): the first LB predecessor states were loaded
-    //      before the ranking; keep walking LB at a time until an inclusive prefix is met.
-    //      (Measured on B200: wider batches, an early spin before the ranking, and a
-    //      status-word protocol with fences were all slower than this.) -------------------
+    // ---- finish the walk (blocking), publish the inclusive prefix ---------------------------
     if (tid < RADIX) {
-        uint32_t excl = 0;
-        bool aborted  = false;
         if (tile > 0) {
-            int64_t p      = (int64_t)tile - 1;
             uint32_t spins = 0;
-            bool done      = false;
             while (true) {
-                int consumed = 0;
-                bool stopped = false;
-#pragma unroll
-                for (int j = 0; j < LB; ++j) {
-                    const uint32_t f = lbv[j] >> FLAG_SHIFT;
-                    if (done || stopped) continue;
-                    if (f == FLAG_EMPTY) {
-                        stopped = true;            // predecessor not published yet: poll it again
-                    } else if (f == FLAG_ABORT) {
-                        aborted = done = true;
-                    } else {
-                        excl += lbv[j] & VALUE_MASK;
-                        ++consumed;
-                        if (f == FLAG_INCL) done = true;
-                    }
-                }
-                p -= consumed;
-                if (stopped && consumed == 0 && ++spins >= SPIN_LIMIT) aborted = done = true;
-                if (done) break;
-#pragma unroll
-                for (int j = 0; j < LB; ++j) {
-                    const int64_t q = p - j;
-                    lbv[j] = q >= 0 ? ld_volatile_u32(tile_state + (size_t)q * RADIX + tid) : (FLAG_INCL << FLAG_SHIFT);
-                }
+                lb_consume();
+                if (lb_done) break;
+                if (!lb_progress && ++spins >= SPIN_LIMIT) { lb_abort = true; break; }
+                lb_issue();
             }
+            const bool aborted = lb_abort;
             if (aborted) {
                 st_volatile_u32(tile_state + (size_t)tile * RADIX + tid, FLAG_ABORT << FLAG_SHIFT);
                 s.abort = 1;
@@ -296,7 +319,7 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict_
             uint32_t pos = s.glob_off[d] + i;
             if (pos < n) {  // always true; keeps a corrupted run (watchdog abort upstream) in bounds
                 keys_out[pos] = k;
-                vals_out[pos] = s.vals[i];
+                if (HAS_VALS) vals_out[pos] = s.vals[i];
             }
         }
     }
@@ -305,11 +328,11 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict_
 // Tile geometries compiled in; PSS_PASS_CFG selects one (default 0).
 struct PassConfig {
     int threads, ipt, smem;
-    const void *fn_iota, *fn_vals;
+    const void *fn_vals, *fn_iota, *fn_keys;
 };
 #define PSS_PASS_CONFIG(T, I, B)                                                             \
-    {T, I, (int)sizeof(PassSmem<T, I>), (const void *)onesweep_pass_kernel<T, I, B, true>,    \
-     (const void *)onesweep_pass_kernel<T, I, B, false>}
+    {T, I, (int)sizeof(PassSmem<T, I>), (const void *)onesweep_pass_kernel<T, I, B, 0>,       \
+     (const void *)onesweep_pass_kernel<T, I, B, 1>, (const void *)onesweep_pass_kernel<T, I, B, 2>}
 const PassConfig kPassConfigs[] = {
     PSS_PASS_CONFIG(256, 16, 3),   // 0 (default): 4096-record tiles, 3 CTAs/SM, 16 records in flight per thread
     PSS_PASS_CONFIG(512, 8, 2),    // 1: 4096-record tiles, 2 CTAs/SM
@@ -350,6 +373,7 @@ int RadixSorter::init(int device) {
     tile_items_ = pc.threads * pc.ipt;
     PSS_CUDA_TRY(cudaFuncSetAttribute(pc.fn_iota, cudaFuncAttributeMaxDynamicSharedMemorySize, pc.smem));
     PSS_CUDA_TRY(cudaFuncSetAttribute(pc.fn_vals, cudaFuncAttributeMaxDynamicSharedMemorySize, pc.smem));
+    PSS_CUDA_TRY(cudaFuncSetAttribute(pc.fn_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, pc.smem));
     return PSS_OK;
 }
 
@@ -380,6 +404,46 @@ void RadixSorter::release() {
     ev_ready_      = false;
     tile_capacity_ = 0;
     device_        = -1;
+}
+
+// One keys-only pass: stable partition of `keys` by the 8-bit digit at `shift` (masked).
+int RadixSorter::partition(uint64_t *keys, uint64_t *keys_alt, uint32_t n, int shift, uint32_t mask,
+                           cudaStream_t stream, bool *in_alt) {
+    *in_alt = false;
+    if (n == 0) return PSS_OK;
+    if (n > VALUE_MASK) return fail(PSS_ERR_ARG, "radix partition: n must be < 2^30");
+    PSS_TRY(ensure(n));
+    const uint32_t tiles = (uint32_t)div_up(n, tile_items_);
+    const PassConfig &pc = kPassConfigs[cfg_];
+    PSS_CUDA_TRY(cudaMemsetAsync(d_hist_, 0, RADIX * sizeof(uint32_t), stream));
+    PSS_CUDA_TRY(cudaMemsetAsync(d_ctrl_, 0, CTRL_WORDS * sizeof(uint32_t), stream));
+    PSS_CUDA_TRY(cudaMemsetAsync(d_tile_state_, 0, (size_t)tiles * RADIX * sizeof(uint32_t), stream));
+    int64_t want = div_up(n, (int64_t)HIST_THREADS * HIST_UNROLL);
+    int grid     = (int)std::min<int64_t>(want, (int64_t)num_sms_ * 4);
+    radix_hist_kernel<<<grid, HIST_THREADS, 0, stream>>>(keys, n, shift, 1, mask, d_hist_);
+    PSS_LAUNCH_CHECK();
+    radix_scan_kernel<<<1, RADIX, 0, stream>>>(d_hist_, d_bin_base_, d_ctrl_, n);
+    PSS_LAUNCH_CHECK();
+    // A constant digit would make the pass a plain copy; it is not worth a host round trip
+    // to find out, so the pass always runs.
+    const uint32_t *vals_arg = nullptr, *base_arg = d_bin_base_;
+    uint32_t *vout = nullptr;
+    uint32_t n_arg = n, mask_arg = mask;
+    int shift_arg = shift, slot_arg = 0;
+    void *args[] = {&keys, &keys_alt, &vals_arg, &vout, &n_arg, &shift_arg, &mask_arg, &base_arg,
+                    &d_tile_state_, &d_ctrl_, &slot_arg};
+    PSS_CUDA_TRY(cudaLaunchKernel(pc.fn_keys, dim3(tiles), dim3(pc.threads), args, (size_t)pc.smem, stream));
+    count_launch();
+    *in_alt = true;
+    return PSS_OK;
+}
+
+// Reads back the look-back watchdog flag (synchronises the stream).
+int RadixSorter::poll_error(cudaStream_t stream) {
+    PSS_CUDA_TRY(cudaMemcpyAsync(h_ctrl_, d_ctrl_, CTRL_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    PSS_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (h_ctrl_[CTRL_ERROR]) return fail(PSS_ERR_CUDA, "radix sort: look-back watchdog fired");
+    return PSS_OK;
 }
 
 int RadixSorter::sort(uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, uint32_t *vals_alt,

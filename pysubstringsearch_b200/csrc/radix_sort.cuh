@@ -49,6 +49,14 @@ public:
              uint32_t n, int begin_bit, int end_bit, bool iota_vals, cudaStream_t stream,
              bool *in_alt, SortProfile *prof);
 
+    // Stable partition of keys by one 8-bit digit ((key >> shift) & mask), keys only; the
+    // result is in keys_alt (*in_alt = true).  Does not synchronise; the look-back
+    // watchdog flag of this pass is read by poll_error().
+    int partition(uint64_t *keys, uint64_t *keys_alt, uint32_t n, int shift, uint32_t mask,
+                  cudaStream_t stream, bool *in_alt);
+
+    int poll_error(cudaStream_t stream);
+
     int device() const { return device_; }
 
 private:

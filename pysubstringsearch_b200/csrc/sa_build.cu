@@ -119,6 +119,29 @@ gather_kernel(const uint32_t *__restrict__ idx, const uint32_t *__restrict__ grp
 }
 
 // ------------------------------------------------------------------------------------
+// Rank scatter ISA[index] = rank from (index << 32 | rank) pairs that were partitioned by
+// the top bits of the index: concurrently running CTAs then write into one window of ISA
+// that fits in L2, so every 32-byte sector reaches DRAM once, fully written, instead of
+// being read-modified-written once per 4-byte rank.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+isa_scatter_kernel(const uint64_t *__restrict__ pairs, uint32_t n_pairs, uint32_t *__restrict__ isa) {
+    constexpr int U = 4;
+    const uint32_t base = blockIdx.x * 256 * U + threadIdx.x;
+    uint64_t v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint32_t k = base + u * 256;
+        v[u] = k < n_pairs ? ld_stream_u64(pairs + k) : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint32_t k = base + u * 256;
+        if (k < n_pairs) isa[(uint32_t)(v[u] >> 32)] = (uint32_t)v[u];
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // Segmented re-rank after a sort.  For sorted position k (old group rank g = key >> gs):
 //   A(k) = last k' <= k that starts an old group,  B(k) = last k' <= k that starts a new
 //   group (new group = run of equal full keys).  SA position p = g + (k - A), new group
@@ -262,7 +285,8 @@ rerank_scan_kernel(uint32_t *__restrict__ tile_aggr, uint32_t tiles, uint32_t *_
 __global__ void __launch_bounds__(RR_THREADS)
 rerank_apply_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t n_active,
                     int gs, int first, const uint32_t *__restrict__ tile_prefix, uint32_t *__restrict__ isa,
-                    int32_t *__restrict__ sa, uint32_t *__restrict__ out_idx, uint32_t *__restrict__ out_grp) {
+                    uint64_t *__restrict__ pairs_out, int32_t *__restrict__ sa, uint32_t *__restrict__ out_idx,
+                    uint32_t *__restrict__ out_grp) {
     __shared__ RerankTile tile;
     __shared__ Tup s_warp[RR_THREADS / 32];
     const uint32_t base = blockIdx.x * RR_TILE;
@@ -303,14 +327,21 @@ rerank_apply_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
         const uint32_t g = first ? 0u : (uint32_t)(tile.k[RerankTile::slot(loc + 1)] >> gs);
         const uint32_t p  = g + (k - A);   // final SA slot of this record inside its old group
         const uint32_t ng = g + (B - A);   // rank of its new group = SA slot of the group's head
+        // New rank of the suffix (1-based; 0 is "past the end"): the group's rank, or the
+        // suffix's final SA slot if it is alone in its group.
+        const uint32_t rank1 = ((f & 4u) ? ng : p) + 1;
         if (f & 4u) {
             const uint32_t c = run.s++;
             out_idx[c] = idx[e];
             out_grp[c] = ng;
-            if (first || ng != g) isa[idx[e]] = ng + 1;
         } else {
             sa[p] = (int32_t)idx[e];
-            if (first || p != g) isa[idx[e]] = p + 1;
+        }
+        if (pairs_out) {
+            // large rounds: the scatter into ISA is done later, partitioned by index window
+            pairs_out[k] = ((uint64_t)idx[e] << 32) | rank1;
+        } else if (first || rank1 != g + 1) {
+            isa[idx[e]] = rank1;
         }
     }
 }
@@ -472,6 +503,8 @@ int SaBuilder::build_device(const uint8_t *d_text, int32_t n, int32_t *d_sa, cud
     PSS_TRY(sorter_.sort(keys_a_, keys_b_, vals_a_, vals_b_, un, 0, m * b, /*iota=*/true, s, &in_alt, &prof));
     record_passes(0, un);
 
+    uint32_t partition_min = 1u << 22;
+    if (const char *e = std::getenv("PSS_PARTITION_MIN")) partition_min = (uint32_t)std::strtoul(e, nullptr, 10);
     uint32_t  n_active = un;
     uint32_t *v_sorted = in_alt ? vals_b_ : vals_a_;
     uint32_t *v_free   = in_alt ? vals_a_ : vals_b_;
@@ -482,12 +515,27 @@ int SaBuilder::build_device(const uint8_t *d_text, int32_t n, int32_t *d_sa, cud
         PSS_LAUNCH_CHECK();
         rerank_scan_kernel<<<1, RS_THREADS, 0, s>>>(tile_aggr_, tiles, d_small_ + SM_SCALARS);
         PSS_LAUNCH_CHECK();
+        // Above the threshold the rank scatter is partitioned (pairs → one keys-only onesweep
+        // pass on the index's top 8 bits → windowed scatter); below it the direct scatter
+        // is cheaper than the extra launches.
+        const bool partitioned = n_active >= partition_min;
+        uint64_t *k_other = (k_sorted == keys_a_) ? keys_b_ : keys_a_;
         rerank_apply_kernel<<<tiles, RR_THREADS, 0, s>>>(k_sorted, v_sorted, n_active, rbits, first ? 1 : 0,
-                                                         tile_aggr_, isa_, d_sa, v_free, grp_);
+                                                         tile_aggr_, isa_, partitioned ? k_other : nullptr, d_sa,
+                                                         v_free, grp_);
         PSS_LAUNCH_CHECK();
+        if (partitioned) {
+            bool alt = false;
+            const int ibits = bit_width_u64((uint64_t)un - 1);
+            const int shift = 32 + std::max(0, ibits - RADIX_BITS);
+            PSS_TRY(sorter_.partition(k_other, k_sorted, n_active, shift, (uint32_t)(RADIX - 1), s, &alt));
+            isa_scatter_kernel<<<(unsigned)div_up(n_active, 256 * 4), 256, 0, s>>>(alt ? k_sorted : k_other, n_active, isa_);
+            PSS_LAUNCH_CHECK();
+        }
         PSS_CUDA_TRY(cudaMemcpyAsync(h_small_ + SM_SCALARS, d_small_ + SM_SCALARS, sizeof(uint32_t),
                                      cudaMemcpyDeviceToHost, s));
         PSS_CUDA_TRY(cudaStreamSynchronize(s));
+        if (partitioned) PSS_TRY(sorter_.poll_error(s));
         n_active = h_small_[SM_SCALARS];
         return PSS_OK;
     };

@@ -32,6 +32,10 @@ for _ in range(repeat):
         [int(st.active_per_round[i]) for i in range(st.rounds + 1)]))
     tot_b = sum(24.0 * ps[i].n_records for i in range(st.n_pass_stats))
     print("pass GB/s avg %.1f" % (tot_b / (st.sort_ms * 1e-3) / 1e9))
+    if os.environ.get("PSS_PRINT_PASSES"):
+        for i in range(st.n_pass_stats):
+            q = ps[i]
+            print("  round %d shift %2d n=%10d %.3f ms %7.1f GB/s" % (q.round, q.shift, q.n_records, q.ms, 24.0 * q.n_records / (q.ms * 1e-3) / 1e9))
 if do_search:
     pats = synth.config2_queries(text, nq=10000, seed=7)
     with tempfile.TemporaryDirectory() as d:
