@@ -163,6 +163,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from pysubstringsearch_b200 import capi as pss   # ctypes binding of include/pss.h
+    from pysubstringsearch_b200 import distributed as D
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -244,17 +245,11 @@ def run_ours(args):
             break
         k = n_entries.value
         if world > 1:
-            # gather the per-chunk hit tuples to rank 0 (NCCL): counts, then one padded all_gather
-            cnt = torch.tensor([k], dtype=torch.int64, device=dev)
-            cnts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-            dist.all_gather(cnts, cnt)
-            kmax = int(max(int(c.item()) for c in cnts))
-            pack = torch.zeros((4, max(kmax, 1)), dtype=torch.int32, device=dev)
-            for i in range(4):
-                pack[i, :k] = outs[i][:k]
-            gathered = [torch.empty_like(pack) for _ in range(world)] if rank == 0 else None
-            dist.gather(pack, gathered, dst=0)
+            # the one exchange step of the path: per-chunk hit tuples → rank 0 over NCCL
+            parts = D.gather_hits(outs[0][:k], outs[1][:k], outs[2][:k], outs[3][:k], dst=0)
             torch.cuda.synchronize()
+            if parts is not None:
+                k = sum(int(p.shape[1]) for p in parts)
         return k, n_hits.value
 
     def build_device():
