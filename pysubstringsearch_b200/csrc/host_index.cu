@@ -309,6 +309,16 @@ struct HostSink : SearchSink {
         res->used += count;
         return PSS_OK;
     }
+    int deliver_host(int64_t count, const int32_t *, const int32_t *c, const uint32_t *s, const uint32_t *e,
+                     cudaStream_t) override {
+        if (count == 0) return PSS_OK;
+        PSS_TRY(res->ensure(res->used + count));
+        std::memcpy(res->chunk() + res->used, c, (size_t)count * 4);
+        std::memcpy(res->start() + res->used, s, (size_t)count * 4);
+        std::memcpy(res->end() + res->used, e, (size_t)count * 4);
+        res->used += count;
+        return PSS_OK;
+    }
 };
 
 // Writes straight into caller-provided device buffers (one-process-per-GPU + NCCL gather).

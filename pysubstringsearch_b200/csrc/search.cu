@@ -2,6 +2,7 @@
 #include "search.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace pss {
@@ -255,11 +256,204 @@ compact_kernel(const uint32_t *__restrict__ flag, const uint32_t *__restrict__ l
     }
 }
 
+
+// ------------------------------------------------------------------------------------
+// Small-batch path: one CTA answers a handful of (query, chunk) pairs end to end — bounds,
+// extraction, dedup (bitonic sort in shared memory) and compaction — so that a single
+// `Reader.search` costs one kernel launch and one device→host copy instead of ~15 launches.
+// Falls back (status = 1) when the pairs have more than SMALL_CAP matching suffixes.
+// ------------------------------------------------------------------------------------
+constexpr int SMALL_THREADS   = 1024;
+constexpr int SMALL_CAP       = 8192;   // matching suffixes handled in shared memory
+constexpr int SMALL_MAX_PAIRS = 64;
+
+struct SmallHeader {
+    uint32_t status;      // 0 = answered, 1 = too many hits (use the general path)
+    uint32_t n_hits;
+    uint32_t n_entries;
+    uint32_t reserved;
+    uint32_t pair_entries[SMALL_MAX_PAIRS];
+};
+// Packed result buffer: header, then query / chunk / start / end arrays of SMALL_CAP each.
+constexpr size_t SMALL_OUT_BYTES = sizeof(SmallHeader) + 4 * (size_t)SMALL_CAP * sizeof(uint32_t);
+
+struct SmallSmem {
+    uint64_t key[SMALL_CAP];       // (pair << 43) | (entry start << 13) | hit index
+    uint32_t end[SMALL_CAP];       // entry end, by hit index
+    uint32_t start[SMALL_CAP];     // bit 31 = first hit of its entry, low bits = entry start
+    uint32_t lb[SMALL_MAX_PAIRS], cnt[SMALL_MAX_PAIRS], off[SMALL_MAX_PAIRS + 1], pair_entries[SMALL_MAX_PAIRS];
+    uint32_t warp_sum[SMALL_THREADS / 32];
+    uint32_t total;
+};
+
+__global__ void __launch_bounds__(SMALL_THREADS, 1)
+small_search_kernel(const DeviceChunk *__restrict__ chunks, int nc, const uint8_t *__restrict__ patterns,
+                    const int64_t *__restrict__ pat_off, uint32_t npairs, uint32_t *__restrict__ lb_out,
+                    uint32_t *__restrict__ cnt_out, unsigned char *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmallSmem &s = *reinterpret_cast<SmallSmem *>(smem_raw);
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    SmallHeader *hdr   = reinterpret_cast<SmallHeader *>(out);
+    int32_t  *o_query  = reinterpret_cast<int32_t *>(out + sizeof(SmallHeader));
+    int32_t  *o_chunk  = o_query + SMALL_CAP;
+    uint32_t *o_start  = reinterpret_cast<uint32_t *>(o_chunk + SMALL_CAP);
+    uint32_t *o_end    = o_start + SMALL_CAP;
+
+    // ---- bounds: one warp per pair (same comparisons as bounds_kernel) ---------------------
+    for (uint32_t pair = warp; pair < npairs; pair += SMALL_THREADS / 32) {
+        const uint32_t q = pair / (uint32_t)nc, c = pair % (uint32_t)nc;
+        const uint8_t *P = patterns + pat_off[q];
+        const uint32_t m = (uint32_t)(pat_off[q + 1] - pat_off[q]);
+        const uint8_t *text = chunks[c].text;
+        const int32_t *sa   = chunks[c].sa;
+        const uint32_t n    = chunks[c].n;
+        const uint32_t pc0  = lane < m ? (uint32_t)__ldg(P + lane) : 0u;
+        uint32_t lo = 0, hi = n;
+        while (lo < hi) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (cmp_suffix(text, n, (uint32_t)__ldg(sa + mid), P, m, pc0, lane) < 0) lo = mid + 1;
+            else hi = mid;
+        }
+        const uint32_t lb = lo;
+        hi = n;
+        while (lo < hi) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (cmp_suffix(text, n, (uint32_t)__ldg(sa + mid), P, m, pc0, lane) <= 0) lo = mid + 1;
+            else hi = mid;
+        }
+        if (lane == 0) {
+            s.lb[pair] = lb;
+            s.cnt[pair] = lo - lb;
+            lb_out[pair] = lb;
+            cnt_out[pair] = lo - lb;
+        }
+    }
+    if (tid < SMALL_MAX_PAIRS) s.pair_entries[tid] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        uint64_t run = 0;
+        for (uint32_t p = 0; p < npairs; ++p) {
+            s.off[p] = (uint32_t)min(run, (uint64_t)0xFFFFFFFFu);
+            run += s.cnt[p];
+        }
+        s.off[npairs] = (uint32_t)min(run, (uint64_t)0xFFFFFFFFu);
+        s.total = (uint32_t)min(run, (uint64_t)0xFFFFFFFFu);
+    }
+    __syncthreads();
+    const uint32_t H = s.total;
+    if (H > SMALL_CAP) {
+        if (tid == 0) { hdr->status = 1; hdr->n_hits = H; hdr->n_entries = 0; }
+        return;
+    }
+    uint32_t P2 = 1;
+    while (P2 < H) P2 <<= 1;
+
+    // ---- extract: entry boundaries of every matching suffix ---------------------------------
+    for (uint32_t f = tid; f < P2; f += SMALL_THREADS) {
+        uint64_t key = ~0ull;
+        if (f < H) {
+            uint32_t p = 0;
+            while (s.off[p + 1] <= f) ++p;
+            const uint32_t c    = p % (uint32_t)nc;
+            const uint8_t *text = chunks[c].text;
+            const uint32_t n    = chunks[c].n;
+            const uint32_t pos  = (uint32_t)__ldg(chunks[c].sa + s.lb[p] + (f - s.off[p]));
+            s.end[f]   = next_newline(text, n, pos);
+            s.start[f] = 0;
+            key = ((uint64_t)p << 43) | ((uint64_t)line_begin(text, pos) << 13) | f;
+        }
+        s.key[f] = key;
+    }
+    __syncthreads();
+
+    // ---- dedup: bitonic sort by (pair, entry start, hit index); the head of every
+    //      (pair, entry start) run is the entry's first hit in SA order -------------------------
+    for (uint32_t k = 2; k <= P2; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = tid; i < P2; i += SMALL_THREADS) {
+                const uint32_t x = i ^ j;
+                if (x > i) {
+                    const uint64_t a = s.key[i], b = s.key[x];
+                    if ((a > b) == ((i & k) == 0)) { s.key[i] = b; s.key[x] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t k = tid; k < H; k += SMALL_THREADS) {
+        const uint64_t cur = s.key[k];
+        if (k == 0 || (s.key[k - 1] >> 13) != (cur >> 13))
+            s.start[(uint32_t)cur & (SMALL_CAP - 1)] = 0x80000000u | (uint32_t)((cur >> 13) & 0x3FFFFFFFu);
+    }
+    __syncthreads();
+
+    // ---- compaction in hit order = (query, chunk, SA order) -------------------------------------
+    constexpr int PER = SMALL_CAP / SMALL_THREADS;
+    const uint32_t base = tid * PER;
+    uint32_t kept = 0;
+#pragma unroll
+    for (int e = 0; e < PER; ++e)
+        if (base + e < H) kept += s.start[base + e] >> 31;
+    uint32_t incl = kept;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += y;
+    }
+    if (lane == 31) s.warp_sum[warp] = incl;
+    __syncthreads();
+    uint32_t pre = 0, tot = 0;
+    for (uint32_t w = 0; w < SMALL_THREADS / 32; ++w) {
+        const uint32_t t = s.warp_sum[w];
+        if (w < warp) pre += t;
+        tot += t;
+    }
+    uint32_t o = pre + incl - kept;
+    if (base < H) {
+        uint32_t p = 0;
+        while (s.off[p + 1] <= base) ++p;
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            const uint32_t f = base + e;
+            if (f >= H) break;
+            while (s.off[p + 1] <= f) ++p;
+            const uint32_t v = s.start[f];
+            if (v >> 31) {
+                o_query[o] = (int32_t)(p / (uint32_t)nc);
+                o_chunk[o] = chunks[p % (uint32_t)nc].global_id;
+                o_start[o] = v & 0x7FFFFFFFu;
+                o_end[o]   = s.end[f];
+                atomicAdd(&s.pair_entries[p], 1u);
+                ++o;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < SMALL_MAX_PAIRS) hdr->pair_entries[tid] = s.pair_entries[tid];
+    if (tid == 0) { hdr->status = 0; hdr->n_hits = H; hdr->n_entries = tot; }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------
+int SearchSink::deliver_host(int64_t count, const int32_t *q, const int32_t *c, const uint32_t *s, const uint32_t *e,
+                             cudaStream_t st) {
+    int32_t *dq = nullptr, *dc = nullptr;
+    uint32_t *ds = nullptr, *de = nullptr;
+    PSS_TRY(reserve(count, &dq, &dc, &ds, &de));
+    if (count) {
+        if (dq) PSS_CUDA_TRY(cudaMemcpyAsync(dq, q, count * 4, cudaMemcpyHostToDevice, st));
+        if (dc) PSS_CUDA_TRY(cudaMemcpyAsync(dc, c, count * 4, cudaMemcpyHostToDevice, st));
+        PSS_CUDA_TRY(cudaMemcpyAsync(ds, s, count * 4, cudaMemcpyHostToDevice, st));
+        PSS_CUDA_TRY(cudaMemcpyAsync(de, e, count * 4, cudaMemcpyHostToDevice, st));
+    }
+    PSS_TRY(commit(count, st));
+    PSS_CUDA_TRY(cudaStreamSynchronize(st));
+    return PSS_OK;
+}
+
 int Searcher::init(int device) {
     if (device_ >= 0) return PSS_OK;
     if (device < 0) device = default_device();
@@ -273,6 +467,12 @@ int Searcher::init(int device) {
     for (auto &e : ev_) PSS_CUDA_TRY(cudaEventCreate(&e));
     PSS_CUDA_TRY(cudaMalloc(&d_scalar_, 16 * sizeof(uint32_t)));
     PSS_CUDA_TRY(cudaMallocHost(&h_scalar_, 16 * sizeof(uint32_t)));
+    PSS_CUDA_TRY(cudaMalloc(&d_small_out_, SMALL_OUT_BYTES));
+    PSS_CUDA_TRY(cudaMallocHost(&h_small_out_, SMALL_OUT_BYTES));
+    PSS_CUDA_TRY(cudaFuncSetAttribute(small_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(SmallSmem)));
+    small_path_ = true;
+    if (const char *e = std::getenv("PSS_SMALL_PATH")) small_path_ = std::atoi(e) != 0;
     PSS_TRY(sorter_.init(device_));
     return PSS_OK;
 }
@@ -288,6 +488,9 @@ void Searcher::release() {
     if (h_pair_first_) cudaFreeHost(h_pair_first_);
     cudaFree(d_keys_); cudaFree(d_keys_alt_); cudaFree(d_vals_); cudaFree(d_vals_alt_);
     cudaFree(d_end_); cudaFree(d_flag_); cudaFree(d_tile_sum_); cudaFree(d_scalar_);
+    cudaFree(d_small_out_);
+    if (h_small_out_) cudaFreeHost(h_small_out_);
+    d_small_out_ = h_small_out_ = nullptr;
     if (h_scalar_) cudaFreeHost(h_scalar_);
     for (auto &e : ev_)
         if (e) cudaEventDestroy(e);
@@ -380,11 +583,42 @@ int Searcher::search(const uint8_t *d_patterns, const int64_t *d_offsets, int32_
     for (const auto &c : chunks_) max_n = std::max(max_n, c.n);
     const int sbits = std::max(1, bit_width_u64((uint64_t)max_n - 1));
 
+    // ---- small batches: one fused kernel, one device→host copy -------------------------------
+    bool have_bounds = false;
+    if (small_path_ && npairs <= (uint32_t)SMALL_MAX_PAIRS) {
+        PSS_CUDA_TRY(cudaEventRecord(ev_[0], s));
+        small_search_kernel<<<1, SMALL_THREADS, sizeof(SmallSmem), s>>>(d_chunks_, nc, d_patterns, d_offsets, npairs, d_lb_,
+                                                                       d_cnt_, d_small_out_);
+        PSS_LAUNCH_CHECK();
+        PSS_CUDA_TRY(cudaEventRecord(ev_[1], s));
+        PSS_CUDA_TRY(cudaMemcpyAsync(h_small_out_, d_small_out_, SMALL_OUT_BYTES, cudaMemcpyDeviceToHost, s));
+        PSS_CUDA_TRY(cudaStreamSynchronize(s));
+        const SmallHeader *hdr = reinterpret_cast<const SmallHeader *>(h_small_out_);
+        if (hdr->status == 0) {
+            const int32_t *hq  = reinterpret_cast<const int32_t *>(h_small_out_ + sizeof(SmallHeader));
+            const int32_t *hc  = hq + SMALL_CAP;
+            const uint32_t *hs = reinterpret_cast<const uint32_t *>(hc + SMALL_CAP);
+            const uint32_t *he = hs + SMALL_CAP;
+            if (n_hits) *n_hits = hdr->n_hits;
+            if (per_pair_count)
+                for (uint32_t p = 0; p < npairs; ++p) per_pair_count[p] = hdr->pair_entries[p];
+            if (times) {
+                float ms = 0.f;
+                PSS_CUDA_TRY(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
+                times->ms_bounds = ms;   // the fused kernel: bounds + extract + dedup
+            }
+            return sink->deliver_host(hdr->n_entries, hq, hc, hs, he, s);
+        }
+        have_bounds = true;   // too many hits: lb/cnt are already in d_lb_/d_cnt_
+    }
+
     // ---- bounds -----------------------------------------------------------------------
     PSS_CUDA_TRY(cudaEventRecord(ev_[0], s));
+    if (!have_bounds) {
     bounds_kernel<<<(unsigned)div_up((int64_t)npairs * 32, BD_THREADS), BD_THREADS, 0, s>>>(
         d_chunks_, nc, d_patterns, d_offsets, npairs, d_lb_, d_cnt_);
     PSS_LAUNCH_CHECK();
+    }
     PSS_CUDA_TRY(cudaEventRecord(ev_[1], s));
     PSS_CUDA_TRY(cudaMemcpyAsync(h_cnt_, d_cnt_, npairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     PSS_CUDA_TRY(cudaStreamSynchronize(s));

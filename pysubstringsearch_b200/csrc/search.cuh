@@ -42,6 +42,10 @@ struct SearchSink {
                         uint32_t **d_end) = 0;
     // Called after the compaction kernel has been enqueued on `stream`.
     virtual int commit(int64_t count, cudaStream_t stream) = 0;
+    // Small-batch path: the entries are already in (pinned) host memory.  The default
+    // forwards them through reserve()/commit(); host sinks override it with a plain copy.
+    virtual int deliver_host(int64_t count, const int32_t *query, const int32_t *chunk, const uint32_t *start,
+                             const uint32_t *end, cudaStream_t stream);
 };
 
 class Searcher {
@@ -83,6 +87,8 @@ private:
     uint32_t *d_vals_ = nullptr, *d_vals_alt_ = nullptr;
     uint32_t *d_end_ = nullptr, *d_flag_ = nullptr, *d_tile_sum_ = nullptr;
     uint32_t *d_scalar_ = nullptr, *h_scalar_ = nullptr;
+    unsigned char *d_small_out_ = nullptr, *h_small_out_ = nullptr;   // small-batch path result block
+    bool      small_path_ = true;
     cudaEvent_t ev_[8] = {};
 };
 
