@@ -81,7 +81,7 @@ typedef struct pss_pass_stat {
     int32_t  round;        /* 0 = initial packed-prefix sort, r >= 1 = doubling round r */
     int32_t  pass;         /* digit index inside the round's sort */
     int32_t  shift;        /* bit offset of the 8-bit digit */
-    int32_t  reserved;
+    int32_t  reserved;     /* digit spread: expected distinct digits per warp x1000 */
     int64_t  n_records;    /* records entering the pass (N_active) */
     float    ms;           /* CUDA-event duration of the pass kernel */
     float    reserved2;

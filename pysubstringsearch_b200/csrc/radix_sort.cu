@@ -18,6 +18,7 @@ constexpr uint32_t SPIN_LIMIT = 1u << 22;
 constexpr int CTRL_TICKET  = 0;   // [0..8)
 constexpr int CTRL_ERROR   = 8;
 constexpr int CTRL_TRIVIAL = 16;  // [16..24)
+constexpr int CTRL_MAXBIN  = 24;  // [24..32) digit spread (expected distinct digits per warp x1000)
 constexpr int CTRL_WORDS   = 32;
 
 // ------------------------------------------------------------------------------------
@@ -82,13 +83,17 @@ __global__ void __launch_bounds__(RADIX)
 radix_scan_kernel(const uint32_t *__restrict__ g_hist, uint32_t *__restrict__ bin_base,
                   uint32_t *__restrict__ ctrl, uint32_t n) {
     __shared__ uint32_t s_warp[RADIX / 32];
-    __shared__ uint32_t s_trivial;
+    __shared__ uint32_t s_trivial, s_max;
     const int p = blockIdx.x;
     const uint32_t t = threadIdx.x, lane = lane_id(), warp = t >> 5;
-    if (t == 0) s_trivial = 0;
+    if (t == 0) { s_trivial = 0; s_max = 0; }
     __syncthreads();
     uint32_t c = g_hist[p * RADIX + t];
     if (c == n) s_trivial = 1;
+    // Expected number of distinct digit values among the 32 records a warp ranks at once,
+    // x1000: sum over bins of 1 - (1 - p_bin)^32.  MATCH.ANY's latency grows with it.
+    const float pb = (float)c / (float)n;
+    atomicAdd(&s_max, (uint32_t)(1000.f * (1.f - __powf(1.f - pb, 32.f)) + 0.5f));
     uint32_t incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -100,7 +105,10 @@ radix_scan_kernel(const uint32_t *__restrict__ g_hist, uint32_t *__restrict__ bi
     uint32_t add = 0;
     for (uint32_t w = 0; w < warp; ++w) add += s_warp[w];
     bin_base[p * RADIX + t] = add + incl - c;
-    if (t == 0) ctrl[CTRL_TRIVIAL + p] = s_trivial;
+    if (t == 0) {
+        ctrl[CTRL_TRIVIAL + p] = s_trivial;
+        ctrl[CTRL_MAXBIN + p]  = s_max;   // digit spread: picks the ranking variant
+    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -123,7 +131,11 @@ struct PassSmem {
 // prefix over tiles 0..tile (INCL).  One word carries flag and value, so no fence is needed.
 // MODE: 0 = (key, value) records, 1 = values are 0..n-1 (generated, not loaded),
 //       2 = keys only (used to partition (index, rank) pairs before the rank scatter).
-template <int THREADS, int IPT, int MIN_BLOCKS, int MODE>
+// BALLOT: how the lanes holding the same digit find each other.  false = the hardware
+// MATCH.ANY instruction, whose latency grows with the number of distinct digits in the warp
+// (fast for skewed digits such as packed text); true = 8 independent ballots, one per
+// digit bit, AND-ed together — a fixed cost that wins on uniformly random digits (ranks).
+template <int THREADS, int IPT, int MIN_BLOCKS, int MODE, bool BALLOT>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ keys_out,
                      const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out,
@@ -266,7 +278,18 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict_
     for (int j = 0; j < IPT; ++j) {
         const uint32_t d     = (uint32_t)(key[j] >> shift) & digit_mask;
         const uint32_t bs    = s.bin_start[d];
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        uint32_t peers;
+        if (BALLOT) {
+            peers = 0xffffffffu;
+#pragma unroll
+            for (int b = 0; b < RADIX_BITS; ++b) {
+                const bool bit    = (d >> b) & 1u;
+                const uint32_t vm = __ballot_sync(0xffffffffu, bit);
+                peers &= bit ? vm : ~vm;
+            }
+        } else {
+            peers = __match_any_sync(0xffffffffu, d);
+        }
         const int leader     = __ffs(peers) - 1;
         uint32_t old         = 0;
         if ((int)lane == leader) {
@@ -328,11 +351,13 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict_
 // Tile geometries compiled in; PSS_PASS_CFG selects one (default 0).
 struct PassConfig {
     int threads, ipt, smem;
-    const void *fn_vals, *fn_iota, *fn_keys;
+    const void *fn[3][2];   // [MODE][BALLOT]
 };
-#define PSS_PASS_CONFIG(T, I, B)                                                             \
-    {T, I, (int)sizeof(PassSmem<T, I>), (const void *)onesweep_pass_kernel<T, I, B, 0>,       \
-     (const void *)onesweep_pass_kernel<T, I, B, 1>, (const void *)onesweep_pass_kernel<T, I, B, 2>}
+#define PSS_PASS_CONFIG(T, I, B)                                                                    \
+    {T, I, (int)sizeof(PassSmem<T, I>),                                                              \
+     {{(const void *)onesweep_pass_kernel<T, I, B, 0, false>, (const void *)onesweep_pass_kernel<T, I, B, 0, true>},  \
+      {(const void *)onesweep_pass_kernel<T, I, B, 1, false>, (const void *)onesweep_pass_kernel<T, I, B, 1, true>},  \
+      {(const void *)onesweep_pass_kernel<T, I, B, 2, false>, (const void *)onesweep_pass_kernel<T, I, B, 2, true>}}}
 const PassConfig kPassConfigs[] = {
     PSS_PASS_CONFIG(256, 16, 3),   // 0 (default): 4096-record tiles, 3 CTAs/SM, 16 records in flight per thread
     PSS_PASS_CONFIG(512, 8, 2),    // 1: 4096-record tiles, 2 CTAs/SM
@@ -371,9 +396,12 @@ int RadixSorter::init(int device) {
     }
     const PassConfig &pc = kPassConfigs[cfg_];
     tile_items_ = pc.threads * pc.ipt;
-    PSS_CUDA_TRY(cudaFuncSetAttribute(pc.fn_iota, cudaFuncAttributeMaxDynamicSharedMemorySize, pc.smem));
-    PSS_CUDA_TRY(cudaFuncSetAttribute(pc.fn_vals, cudaFuncAttributeMaxDynamicSharedMemorySize, pc.smem));
-    PSS_CUDA_TRY(cudaFuncSetAttribute(pc.fn_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, pc.smem));
+    for (int m = 0; m < 3; ++m)
+        for (int b = 0; b < 2; ++b)
+            PSS_CUDA_TRY(cudaFuncSetAttribute(pc.fn[m][b], cudaFuncAttributeMaxDynamicSharedMemorySize, pc.smem));
+    ballot_mode_ = 2;   // 0 = always MATCH.ANY, 1 = always ballots, 2 = per pass from the histogram
+    if (const char *e = std::getenv("PSS_BALLOT")) ballot_mode_ = std::atoi(e);
+    if (const char *e = std::getenv("PSS_SPREAD_THRESHOLD")) spread_threshold_ = (uint32_t)std::atoi(e);
     return PSS_OK;
 }
 
@@ -432,7 +460,9 @@ int RadixSorter::partition(uint64_t *keys, uint64_t *keys_alt, uint32_t n, int s
     int shift_arg = shift, slot_arg = 0;
     void *args[] = {&keys, &keys_alt, &vals_arg, &vout, &n_arg, &shift_arg, &mask_arg, &base_arg,
                     &d_tile_state_, &d_ctrl_, &slot_arg};
-    PSS_CUDA_TRY(cudaLaunchKernel(pc.fn_keys, dim3(tiles), dim3(pc.threads), args, (size_t)pc.smem, stream));
+    // index windows are near-uniform: the ballot ranking is the right one
+    PSS_CUDA_TRY(cudaLaunchKernel(pc.fn[2][ballot_mode_ == 0 ? 0 : 1], dim3(tiles), dim3(pc.threads), args,
+                                  (size_t)pc.smem, stream));
     count_launch();
     *in_alt = true;
     return PSS_OK;
@@ -479,12 +509,18 @@ int RadixSorter::sort(uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, uint32
     PSS_CUDA_TRY(cudaMemcpyAsync(h_ctrl_, d_ctrl_, CTRL_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     PSS_CUDA_TRY(cudaStreamSynchronize(stream));
 
+    uint32_t max_bin[MAX_PASSES];
+    bool     trivial[MAX_PASSES];
+    for (int p = 0; p < MAX_PASSES; ++p) {
+        max_bin[p] = h_ctrl_[CTRL_MAXBIN + p];
+        trivial[p] = h_ctrl_[CTRL_TRIVIAL + p] != 0;
+    }
     uint64_t *kin = keys, *kout = keys_alt;
     uint32_t *vin = vals, *vout = vals_alt;
     bool iota = iota_vals;  // first executed pass generates 0..n-1 instead of reading vin
     int executed = 0;
     for (int p = 0; p < npass; ++p) {
-        if (h_ctrl_[CTRL_TRIVIAL + p]) continue;  // every key has the same digit: order unchanged
+        if (trivial[p]) continue;  // every key has the same digit: order unchanged
         const int shift     = begin_bit + p * RADIX_BITS;
         const uint32_t mask = (p == npass - 1) ? last_mask : (uint32_t)(RADIX - 1);
         PSS_CUDA_TRY(cudaMemsetAsync(d_tile_state_, 0, (size_t)tiles * RADIX * sizeof(uint32_t), stream));
@@ -496,12 +532,14 @@ int RadixSorter::sort(uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, uint32
             int shift_arg = shift, slot_arg = p;
             void *args[] = {&kin, &kout, &vals_arg, &vout, &n_arg, &shift_arg, &mask_arg, &base_arg,
                             &d_tile_state_, &d_ctrl_, &slot_arg};
-            PSS_CUDA_TRY(cudaLaunchKernel(iota ? pc.fn_iota : pc.fn_vals, dim3(tiles), dim3(pc.threads), args,
+            // many distinct digits per warp → ballots (threshold calibrated on B200)
+            const bool ballot = ballot_mode_ == 1 || (ballot_mode_ == 2 && max_bin[p] > spread_threshold_);
+            PSS_CUDA_TRY(cudaLaunchKernel(pc.fn[iota ? 1 : 0][ballot ? 1 : 0], dim3(tiles), dim3(pc.threads), args,
                                           (size_t)pc.smem, stream));
         }
         PSS_LAUNCH_CHECK();
         if (timed) PSS_CUDA_TRY(cudaEventRecord(ev_[2 * executed + 1], stream));
-        if (prof) prof->shift[executed] = shift;
+        if (prof) { prof->shift[executed] = shift; prof->spread[executed] = (int)max_bin[p]; }
         iota = false;
         std::swap(kin, kout);
         std::swap(vin, vout);

@@ -25,6 +25,7 @@ struct SortProfile {
     bool  timed    = false;  // in: record CUDA events around the histogram and every pass
     int   n_passes = 0;      // out: passes executed (constant digits are skipped)
     int   shift[MAX_PASSES] = {};
+    int   spread[MAX_PASSES] = {};  // expected distinct digits per warp x1000 (chooses the ranking variant)
     float ms[MAX_PASSES]    = {};   // valid when timed
     float hist_ms = 0.f;            // valid when timed
 };
@@ -64,6 +65,8 @@ private:
     int       num_sms_       = 0;
     int       cfg_           = 0;     // index into the compiled tile geometries (PSS_PASS_CFG)
     int       tile_items_    = 4096;  // records per tile of the selected geometry
+    int       ballot_mode_   = 2;     // ranking variant: 0 MATCH.ANY, 1 ballots, 2 chosen per pass (PSS_BALLOT)
+    uint32_t  spread_threshold_ = 8000;   // MATCH.ANY only when a warp sees at most ~8 distinct digits
     int64_t   tile_capacity_ = 0;
     uint32_t *d_hist_        = nullptr;  // [MAX_PASSES][RADIX]
     uint32_t *d_bin_base_    = nullptr;  // [MAX_PASSES][RADIX]

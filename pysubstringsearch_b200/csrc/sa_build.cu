@@ -489,7 +489,7 @@ int SaBuilder::build_device(const uint8_t *d_text, int32_t n, int32_t *d_sa, cud
             stats_.sort_ms += prof.ms[p];
             if (profiling_ && (int)pass_stats_.size() < PSS_MAX_PASS_STATS) {
                 pss_pass_stat ps = {};
-                ps.round = round; ps.pass = p; ps.shift = prof.shift[p];
+                ps.round = round; ps.pass = p; ps.shift = prof.shift[p]; ps.reserved = prof.spread[p];
                 ps.n_records = n_rec; ps.ms = prof.ms[p];
                 pass_stats_.push_back(ps);
             }

@@ -35,7 +35,7 @@ for _ in range(repeat):
     if os.environ.get("PSS_PRINT_PASSES"):
         for i in range(st.n_pass_stats):
             q = ps[i]
-            print("  round %d shift %2d n=%10d %.3f ms %7.1f GB/s" % (q.round, q.shift, q.n_records, q.ms, 24.0 * q.n_records / (q.ms * 1e-3) / 1e9))
+            print("  round %d shift %2d spread %5.1f n=%10d %.3f ms %7.1f GB/s" % (q.round, q.shift, q.reserved / 1000.0, q.n_records, q.ms, 24.0 * q.n_records / (q.ms * 1e-3) / 1e9))
 if do_search:
     pats = synth.config2_queries(text, nq=10000, seed=7)
     with tempfile.TemporaryDirectory() as d:
