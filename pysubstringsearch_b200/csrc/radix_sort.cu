@@ -40,6 +40,8 @@ radix_hist_kernel(const uint64_t *__restrict__ keys, uint32_t n, int begin_bit, 
     const uint32_t warps_total = gridDim.x * (HIST_THREADS / 32);
     const uint32_t warp_global = blockIdx.x * (HIST_THREADS / 32) + warp;
 
+    HistLayout h;
+    h.begin_bit = begin_bit; h.npass = npass; h.last_mask = last_mask;
     for (uint64_t base = (uint64_t)warp_global * WARP_SPAN; base < n;
          base += (uint64_t)warps_total * WARP_SPAN) {
         uint64_t k[HIST_UNROLL];
@@ -51,31 +53,11 @@ radix_hist_kernel(const uint64_t *__restrict__ keys, uint32_t n, int begin_bit, 
             k[u]  = ok[u] ? ld_stream_u64(keys + i) : 0ull;
         }
 #pragma unroll
-        for (int u = 0; u < HIST_UNROLL; ++u) {
-            const bool full = (base + u * 32 + 32) <= n;  // warp-uniform
-            for (int p = 0; p < npass; ++p) {
-                uint32_t d = (uint32_t)(k[u] >> (begin_bit + p * RADIX_BITS)) &
-                             (p == npass - 1 ? last_mask : (uint32_t)(RADIX - 1));
-                if (full) {
-                    // Constant digits (high bits of small ranks, padded alphabets) would
-                    // serialise 32 same-address atomics; aggregate them instead.
-                    uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
-                    if (__all_sync(0xffffffffu, d == d0)) {
-                        if (lane == 0) atomicAdd(&s_hist[p * RADIX + d0], 32u);
-                    } else {
-                        atomicAdd(&s_hist[p * RADIX + d], 1u);
-                    }
-                } else if (ok[u]) {
-                    atomicAdd(&s_hist[p * RADIX + d], 1u);
-                }
-            }
-        }
+        for (int u = 0; u < HIST_UNROLL; ++u)
+            hist_accumulate(s_hist, k[u], ok[u], (base + u * 32 + 32) <= n, h);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < npass * RADIX; i += HIST_THREADS) {
-        uint32_t c = s_hist[i];
-        if (c) atomicAdd(&g_hist[i], c);
-    }
+    hist_flush(s_hist, g_hist, npass, HIST_THREADS);
 }
 
 // Exclusive scan of each digit's histogram → bin_base; flag digits with one non-empty bin.
@@ -476,9 +458,14 @@ int RadixSorter::poll_error(cudaStream_t stream) {
     return PSS_OK;
 }
 
+int RadixSorter::hist_reset(cudaStream_t stream) {
+    PSS_CUDA_TRY(cudaMemsetAsync(d_hist_, 0, MAX_PASSES * RADIX * sizeof(uint32_t), stream));
+    return PSS_OK;
+}
+
 int RadixSorter::sort(uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, uint32_t *vals_alt,
                       uint32_t n, int begin_bit, int end_bit, bool iota_vals, cudaStream_t stream,
-                      bool *in_alt, SortProfile *prof) {
+                      bool *in_alt, SortProfile *prof, bool hist_done) {
     *in_alt = false;
     const bool timed = prof && prof->timed;
     if (prof) { prof->n_passes = 0; prof->hist_ms = 0.f; }
@@ -494,14 +481,16 @@ int RadixSorter::sort(uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, uint32
     const uint32_t tiles     = (uint32_t)div_up(n, tile_items_);
     const PassConfig &pc     = kPassConfigs[cfg_];
 
-    PSS_CUDA_TRY(cudaMemsetAsync(d_hist_, 0, MAX_PASSES * RADIX * sizeof(uint32_t), stream));
+    if (!hist_done) PSS_CUDA_TRY(cudaMemsetAsync(d_hist_, 0, MAX_PASSES * RADIX * sizeof(uint32_t), stream));
     PSS_CUDA_TRY(cudaMemsetAsync(d_ctrl_, 0, CTRL_WORDS * sizeof(uint32_t), stream));
     if (timed) PSS_CUDA_TRY(cudaEventRecord(ev_[2 * MAX_PASSES], stream));
     {
-        int64_t want = div_up(n, (int64_t)HIST_THREADS * HIST_UNROLL);
-        int grid     = (int)std::min<int64_t>(want, (int64_t)num_sms_ * 4);
-        radix_hist_kernel<<<grid, HIST_THREADS, 0, stream>>>(keys, n, begin_bit, npass, last_mask, d_hist_);
-        PSS_LAUNCH_CHECK();
+        if (!hist_done) {
+            int64_t want = div_up(n, (int64_t)HIST_THREADS * HIST_UNROLL);
+            int grid     = (int)std::min<int64_t>(want, (int64_t)num_sms_ * 4);
+            radix_hist_kernel<<<grid, HIST_THREADS, 0, stream>>>(keys, n, begin_bit, npass, last_mask, d_hist_);
+            PSS_LAUNCH_CHECK();
+        }
         radix_scan_kernel<<<npass, RADIX, 0, stream>>>(d_hist_, d_bin_base_, d_ctrl_, n);
         PSS_LAUNCH_CHECK();
     }

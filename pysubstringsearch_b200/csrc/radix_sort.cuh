@@ -21,6 +21,51 @@ constexpr int RADIX      = 1 << RADIX_BITS;
 constexpr int MAX_PASSES = 8;
 
 
+// Digit layout of a sort over key bits [begin_bit, end_bit): what a kernel that produces
+// the keys needs in order to accumulate the upfront histograms itself (hist_accumulate).
+struct HistLayout {
+    int      begin_bit = 0, npass = 0;
+    uint32_t last_mask = 0;
+};
+inline HistLayout hist_layout(int begin_bit, int end_bit) {
+    HistLayout h;
+    h.begin_bit = begin_bit;
+    h.npass     = (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS;
+    const int last_bits = (end_bit - begin_bit) - (h.npass - 1) * RADIX_BITS;
+    h.last_mask = (1u << last_bits) - 1u;
+    return h;
+}
+
+#ifdef __CUDACC__
+// Adds one key per lane to the block's shared-memory histograms s_hist[npass][RADIX].
+// `warp_full` (warp-uniform) says all 32 lanes hold a valid key: only then can a digit that
+// is identical across the warp be added with one atomic instead of 32 same-address ones.
+__device__ __forceinline__ void hist_accumulate(uint32_t *s_hist, uint64_t key, bool valid, bool warp_full,
+                                                const HistLayout &h) {
+    const uint32_t lane = threadIdx.x & 31u;
+    for (int p = 0; p < h.npass; ++p) {
+        const uint32_t d = (uint32_t)(key >> (h.begin_bit + p * RADIX_BITS)) &
+                           (p == h.npass - 1 ? h.last_mask : (uint32_t)(RADIX - 1));
+        if (warp_full) {
+            const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
+            if (__all_sync(0xffffffffu, d == d0)) {
+                if (lane == 0) atomicAdd(&s_hist[p * RADIX + d0], 32u);
+            } else {
+                atomicAdd(&s_hist[p * RADIX + d], 1u);
+            }
+        } else if (valid) {
+            atomicAdd(&s_hist[p * RADIX + d], 1u);
+        }
+    }
+}
+__device__ __forceinline__ void hist_flush(const uint32_t *s_hist, uint32_t *g_hist, int npass, int threads) {
+    for (int i = threadIdx.x; i < npass * RADIX; i += threads) {
+        const uint32_t c = s_hist[i];
+        if (c) atomicAdd(&g_hist[i], c);
+    }
+}
+#endif
+
 struct SortProfile {
     bool  timed    = false;  // in: record CUDA events around the histogram and every pass
     int   n_passes = 0;      // out: passes executed (constant digits are skipped)
@@ -48,7 +93,13 @@ public:
     // Synchronises the stream before returning.
     int sort(uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, uint32_t *vals_alt,
              uint32_t n, int begin_bit, int end_bit, bool iota_vals, cudaStream_t stream,
-             bool *in_alt, SortProfile *prof);
+             bool *in_alt, SortProfile *prof, bool hist_done = false);
+
+    // For key-producing kernels that fill the histograms themselves: zero them (hist_reset),
+    // accumulate into d_hist() with hist_accumulate/hist_flush, then sort(..., hist_done = true).
+    int       hist_reset(cudaStream_t stream);
+    uint32_t *d_hist() const { return d_hist_; }
+    int       num_sms() const { return num_sms_; }
 
     // Stable partition of keys by one 8-bit digit ((key >> shift) & mask), keys only; the
     // result is in keys_alt (*in_alt = true).  Does not synchronise; the look-back

@@ -12,7 +12,8 @@ namespace {
 
 // d_small_ layout (32-bit words)
 constexpr int SM_PRESENCE = 0;    // [0..8)   256-bit set of byte values present in the text
-constexpr int SM_SCALARS  = 8;    // [8..16)  [8] = active suffixes after the current re-rank
+constexpr int SM_SCALARS  = 8;    // [8..16)  [8] = active suffixes after the current re-rank, [9] = tile ticket,
+                                  //          [10] = look-back watchdog flag, [11] = active-set append cursor
 constexpr int SM_LUT      = 16;   // [16..144) 256 x u16: byte value → dense code (1..sigma)
 constexpr int SM_WORDS    = 144;
 
@@ -54,19 +55,25 @@ presence_kernel(const uint8_t *__restrict__ text, uint32_t n, uint32_t *__restri
 // Round 0 keys: key(i) = codes of T[i .. i+m) packed big-endian, b bits each, 0 past end.
 // ------------------------------------------------------------------------------------
 constexpr int KG_THREADS = 256;
-constexpr int KG_IPT     = 16;
+constexpr int KG_IPT     = 8;
 constexpr int KG_TILE    = KG_THREADS * KG_IPT;
 
+// Persistent: each CTA walks tiles grid-stride and also accumulates the radix histograms of
+// the keys it produces (so the sort needs no separate histogram pass over them).
 __global__ void __launch_bounds__(KG_THREADS)
 keygen_kernel(const uint8_t *__restrict__ text, uint32_t n, const uint16_t *__restrict__ lut, int b, int m,
-              uint64_t *__restrict__ keys) {
+              uint64_t *__restrict__ keys, HistLayout hl, uint32_t *__restrict__ g_hist) {
     __shared__ uint16_t s_lut[256];
     __shared__ uint16_t s_code[KG_TILE + 64];
     __shared__ uint64_t s_key[KG_TILE + KG_TILE / KG_IPT];  // one pad word per thread row
+    __shared__ uint32_t s_hist[MAX_PASSES * RADIX];
     const uint32_t tid = threadIdx.x;
-    const uint32_t base = blockIdx.x * KG_TILE;
     s_lut[tid] = lut[tid];
+    for (int i = tid; i < hl.npass * RADIX; i += KG_THREADS) s_hist[i] = 0;
     __syncthreads();
+    const uint32_t tiles = (n + KG_TILE - 1) / KG_TILE;
+    for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const uint32_t base = t * KG_TILE;
     for (uint32_t i = tid; i < (uint32_t)(KG_TILE + m); i += KG_THREADS) {
         uint32_t pos = base + i;
         s_code[i] = pos < n ? s_lut[text[pos]] : (uint16_t)0;
@@ -82,11 +89,18 @@ keygen_kernel(const uint8_t *__restrict__ text, uint32_t n, const uint16_t *__re
         w = ((w << b) & mask) | s_code[r0 + j + m];
     }
     __syncthreads();
+    const bool tile_full = base + KG_TILE <= n;
 #pragma unroll
     for (int j = 0; j < KG_IPT; ++j) {
         uint32_t i = j * KG_THREADS + tid;
-        if (base + i < n) keys[base + i] = s_key[(i / KG_IPT) * (KG_IPT + 1) + (i % KG_IPT)];
+        const bool ok = base + i < n;
+        const uint64_t kv = s_key[(i / KG_IPT) * (KG_IPT + 1) + (i % KG_IPT)];
+        if (ok) keys[base + i] = kv;
+        hist_accumulate(s_hist, kv, ok, tile_full, hl);
     }
+    __syncthreads();   // s_code / s_key are reused by the next tile
+    }
+    hist_flush(s_hist, g_hist, hl.npass, KG_THREADS);
 }
 
 // ------------------------------------------------------------------------------------
@@ -95,27 +109,38 @@ keygen_kernel(const uint8_t *__restrict__ text, uint32_t n, const uint16_t *__re
 __global__ void __launch_bounds__(256)
 gather_kernel(const uint32_t *__restrict__ idx, const uint32_t *__restrict__ grp,
               const uint32_t *__restrict__ isa, uint32_t n, uint32_t h, int rbits, uint32_t n_active,
-              uint64_t *__restrict__ keys) {
+              uint64_t *__restrict__ keys, HistLayout hl, uint32_t *__restrict__ g_hist) {
     constexpr int U = 4;
-    const uint32_t base = (blockIdx.x * 256 * U) + threadIdx.x;
-    uint32_t i[U], g[U], r[U];
+    __shared__ uint32_t s_hist[MAX_PASSES * RADIX];
+    for (int i = threadIdx.x; i < hl.npass * RADIX; i += 256) s_hist[i] = 0;
+    __syncthreads();
+    const uint32_t blocks = (n_active + 256 * U - 1) / (256 * U);
+    for (uint32_t blk = blockIdx.x; blk < blocks; blk += gridDim.x) {
+        const uint32_t base = (blk * 256 * U) + threadIdx.x;
+        uint32_t i[U], g[U], r[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        uint32_t k = base + u * 256;
-        i[u] = k < n_active ? ld_stream_u32(idx + k) : 0u;
-        g[u] = k < n_active ? ld_stream_u32(grp + k) : 0u;
-    }
+        for (int u = 0; u < U; ++u) {
+            uint32_t k = base + u * 256;
+            i[u] = k < n_active ? ld_stream_u32(idx + k) : 0u;
+            g[u] = k < n_active ? ld_stream_u32(grp + k) : 0u;
+        }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        uint32_t k = base + u * 256;
-        uint64_t j = (uint64_t)i[u] + h;
-        r[u] = (k < n_active && j < n) ? __ldg(isa + j) : 0u;
-    }
+        for (int u = 0; u < U; ++u) {
+            uint32_t k = base + u * 256;
+            uint64_t j = (uint64_t)i[u] + h;
+            r[u] = (k < n_active && j < n) ? __ldg(isa + j) : 0u;
+        }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        uint32_t k = base + u * 256;
-        if (k < n_active) keys[k] = ((uint64_t)g[u] << rbits) | r[u];
+        for (int u = 0; u < U; ++u) {
+            uint32_t k = base + u * 256;
+            const uint64_t kv = ((uint64_t)g[u] << rbits) | r[u];
+            if (k < n_active) keys[k] = kv;
+            // the warp's 32 keys are consecutive: full iff its last one is in range
+            hist_accumulate(s_hist, kv, k < n_active, (k | 31u) < n_active, hl);
+        }
     }
+    __syncthreads();
+    hist_flush(s_hist, g_hist, hl.npass, 256);
 }
 
 // ------------------------------------------------------------------------------------
@@ -124,20 +149,59 @@ gather_kernel(const uint32_t *__restrict__ idx, const uint32_t *__restrict__ grp
 // that fits in L2, so every 32-byte sector reaches DRAM once, fully written, instead of
 // being read-modified-written once per 4-byte rank.
 // ------------------------------------------------------------------------------------
+// The same pass also extracts the next round's active set — pairs whose bit 31 is set are
+// suffixes that still share a group; their (index, group rank = rank - 1) are appended to
+// out_idx / out_grp.  Taking them from here rather than from the sorted order leaves the
+// active set bucketed by index window as well, so the next round's ISA[i + h] gather reads
+// stay inside an L2-resident window too.  (The order of the active set is irrelevant: the
+// next sort is a full radix sort.)  Space is claimed with one atomicAdd per CTA.
 __global__ void __launch_bounds__(256)
-isa_scatter_kernel(const uint64_t *__restrict__ pairs, uint32_t n_pairs, uint32_t *__restrict__ isa) {
+isa_scatter_kernel(const uint64_t *__restrict__ pairs, uint32_t n_pairs, uint32_t *__restrict__ isa,
+                   uint32_t *__restrict__ out_idx, uint32_t *__restrict__ out_grp, uint32_t *__restrict__ counter) {
     constexpr int U = 4;
-    const uint32_t base = blockIdx.x * 256 * U + threadIdx.x;
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_base;
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    // blocked: a thread owns U consecutive pairs, so that its kept records are written together
+    const uint32_t base = (blockIdx.x * 256 + threadIdx.x) * U;
     uint64_t v[U];
+    uint32_t kept = 0;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        const uint32_t k = base + u * 256;
+        const uint32_t k = base + u;
         v[u] = k < n_pairs ? ld_stream_u64(pairs + k) : 0ull;
+        kept += (uint32_t)(v[u] >> 31) & 1u;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        const uint32_t k = base + u * 256;
-        if (k < n_pairs) isa[(uint32_t)(v[u] >> 32)] = (uint32_t)v[u];
+        const uint32_t k = base + u;
+        if (k < n_pairs) isa[(uint32_t)(v[u] >> 32)] = (uint32_t)v[u] & 0x7FFFFFFFu;
+    }
+    uint32_t incl = kept;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += y;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t pre = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const uint32_t t = s_warp[w];
+        if ((uint32_t)w < warp) pre += t;
+        tot += t;
+    }
+    if (threadIdx.x == 0) s_base = tot ? atomicAdd(counter, tot) : 0u;
+    __syncthreads();
+    uint32_t o = s_base + pre + incl - kept;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if ((v[u] >> 31) & 1u) {
+            out_idx[o] = (uint32_t)(v[u] >> 32);
+            out_grp[o] = ((uint32_t)v[u] & 0x7FFFFFFFu) - 1u;
+            ++o;
+        }
     }
 }
 
@@ -147,7 +211,7 @@ isa_scatter_kernel(const uint64_t *__restrict__ pairs, uint32_t n_pairs, uint32_
 //   group (new group = run of equal full keys).  SA position p = g + (k - A), new group
 //   rank = g + (B - A).  A suffix alone in its new group is final: SA[p] = i.  The rest
 //   are compacted (order preserved) into the next round's active set.
-// Implemented as reduce → scan of tile aggregates → apply over tiles of 2048 records.
+// One pass over tiles of 2048 records: per-tile aggregates are chained by decoupled look-back.
 // ------------------------------------------------------------------------------------
 constexpr int RR_THREADS = 256;
 constexpr int RR_IPT     = 8;
@@ -230,66 +294,39 @@ __device__ __forceinline__ uint32_t rerank_flags(const RerankTile &t, uint32_t u
     return (ho ? 1u : 0u) | (hn ? 2u : 0u) | (keep ? 4u : 0u);
 }
 
-__global__ void __launch_bounds__(RR_THREADS)
-rerank_reduce_kernel(const uint64_t *__restrict__ keys, uint32_t n_active, int gs, int first,
-                     uint32_t *__restrict__ tile_aggr) {
-    __shared__ RerankTile tile;
-    __shared__ Tup s_warp[RR_THREADS / 32];
-    const uint32_t base = blockIdx.x * RR_TILE;
-    rerank_load(tile, keys, base, n_active);
-    Tup agg = {0, 0, 0};
-#pragma unroll
-    for (int e = 0; e < RR_IPT; ++e) {
-        uint32_t loc = threadIdx.x * RR_IPT + e;
-        uint32_t k   = base + loc;
-        if (k < n_active) {
-            uint32_t f = rerank_flags(tile, loc + 1, k, n_active, gs, first != 0);
-            if (f & 1u) agg.a = k + 1;
-            if (f & 2u) agg.b = k + 1;
-            agg.s += (f >> 2) & 1u;
-        }
-    }
-    Tup total;
-    (void)block_excl_scan<RR_THREADS>(agg, s_warp, &total);
-    if (threadIdx.x == 0) {
-        tile_aggr[blockIdx.x * 3 + 0] = total.a;
-        tile_aggr[blockIdx.x * 3 + 1] = total.b;
-        tile_aggr[blockIdx.x * 3 + 2] = total.s;
-    }
+// Look-back state of the single-pass re-rank: two self-validating 64-bit words per tile,
+//   w0 = flag(2) | a(31) | b(31),  w1 = flag(2) | s(32);  flag 1 = the tile's own aggregate,
+//   2 = inclusive prefix over tiles 0..t, 3 = abort.  A reader accepts a pair only when
+//   both flags agree, so no fence is needed between the two stores.
+__device__ __forceinline__ void rr_publish(unsigned long long *state, uint32_t tile, uint32_t flag, const Tup &v) {
+    const unsigned long long w0 = ((unsigned long long)flag << 62) | ((unsigned long long)v.a << 31) | v.b;
+    const unsigned long long w1 = ((unsigned long long)flag << 62) | v.s;
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(state + 2 * (size_t)tile), "l"(w0) : "memory");
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(state + 2 * (size_t)tile + 1), "l"(w1) : "memory");
 }
-
-constexpr int RS_THREADS = 1024;
-__global__ void __launch_bounds__(RS_THREADS)
-rerank_scan_kernel(uint32_t *__restrict__ tile_aggr, uint32_t tiles, uint32_t *__restrict__ scalars) {
-    __shared__ Tup s_warp[RS_THREADS / 32];
-    const uint32_t per = (tiles + RS_THREADS - 1) / RS_THREADS;
-    const uint32_t lo  = min(tiles, threadIdx.x * per);
-    const uint32_t hi  = min(tiles, lo + per);
-    Tup agg = {0, 0, 0};
-    for (uint32_t t = lo; t < hi; ++t) {
-        Tup v = {tile_aggr[t * 3 + 0], tile_aggr[t * 3 + 1], tile_aggr[t * 3 + 2]};
-        agg = tup_comb(agg, v);
-    }
-    Tup total;
-    Tup run = block_excl_scan<RS_THREADS>(agg, s_warp, &total);
-    for (uint32_t t = lo; t < hi; ++t) {
-        Tup v = {tile_aggr[t * 3 + 0], tile_aggr[t * 3 + 1], tile_aggr[t * 3 + 2]};
-        tile_aggr[t * 3 + 0] = run.a;
-        tile_aggr[t * 3 + 1] = run.b;
-        tile_aggr[t * 3 + 2] = run.s;
-        run = tup_comb(run, v);
-    }
-    if (threadIdx.x == 0) scalars[0] = total.s;
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
 
 __global__ void __launch_bounds__(RR_THREADS)
 rerank_apply_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t n_active,
-                    int gs, int first, const uint32_t *__restrict__ tile_prefix, uint32_t *__restrict__ isa,
-                    uint64_t *__restrict__ pairs_out, int32_t *__restrict__ sa, uint32_t *__restrict__ out_idx,
-                    uint32_t *__restrict__ out_grp) {
+                    int gs, int first, unsigned long long *tile_state, uint32_t *scalars,
+                    uint32_t *__restrict__ isa, uint64_t *__restrict__ pairs_out, int32_t *__restrict__ sa,
+                    uint32_t *__restrict__ out_idx, uint32_t *__restrict__ out_grp) {
     __shared__ RerankTile tile;
     __shared__ Tup s_warp[RR_THREADS / 32];
-    const uint32_t base = blockIdx.x * RR_TILE;
+    __shared__ Tup s_excl;
+    __shared__ uint32_t s_tile, s_abort;
+    // single pass: tiles are ticketed in launch order and chained by decoupled look-back
+    if (threadIdx.x == 0) {
+        s_tile  = atomicAdd(&scalars[1], 1u);
+        s_abort = 0;
+    }
+    __syncthreads();
+    const uint32_t tile_id = s_tile;
+    const uint32_t base    = tile_id * RR_TILE;
     rerank_load(tile, keys, base, n_active);
 
     uint32_t flags[RR_IPT];
@@ -312,8 +349,72 @@ rerank_apply_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
     }
     Tup total;
     Tup run = block_excl_scan<RR_THREADS>(agg, s_warp, &total);
-    Tup pre = {tile_prefix[blockIdx.x * 3 + 0], tile_prefix[blockIdx.x * 3 + 1], tile_prefix[blockIdx.x * 3 + 2]};
-    run = tup_comb(pre, run);
+
+    // ---- decoupled look-back over the preceding tiles' aggregates (warp 0, 32 tiles a step) ----
+    if (threadIdx.x < 32) {
+        const uint32_t lane = threadIdx.x;
+        if (lane == 0) rr_publish(tile_state, tile_id, tile_id == 0 ? 2u : 1u, total);
+        Tup excl = {0, 0, 0};
+        bool aborted = false;
+        if (tile_id > 0) {
+            int64_t basep  = (int64_t)tile_id - 1;
+            uint32_t spins = 0;
+            while (true) {
+                const int64_t q = basep - lane;
+                unsigned long long w0 = 2ull << 62, w1 = 2ull << 62;   // before tile 0: inclusive identity
+                if (q >= 0) {
+                    w0 = ld_volatile_u64(tile_state + 2 * (size_t)q);
+                    w1 = ld_volatile_u64(tile_state + 2 * (size_t)q + 1);
+                }
+                const uint32_t f0 = (uint32_t)(w0 >> 62), f1 = (uint32_t)(w1 >> 62);
+                const bool ready  = f0 != 0 && f0 == f1;
+                const uint32_t m_incl  = __ballot_sync(0xffffffffu, ready && f0 == 2u);
+                const uint32_t m_abort = __ballot_sync(0xffffffffu, f0 == 3u || f1 == 3u);
+                const int k_incl       = m_incl ? __ffs(m_incl) - 1 : 32;
+                const uint32_t need    = k_incl >= 31 ? 0xffffffffu : ((2u << k_incl) - 1u);   // lanes 0..k_incl
+                const uint32_t m_wait  = __ballot_sync(0xffffffffu, !ready) & need;
+                if (m_abort & need) { aborted = true; break; }
+                if (m_wait) {
+                    if (++spins > (1u << 22)) { aborted = true; break; }
+                    continue;
+                }
+                Tup v = {0, 0, 0};
+                if ((int)lane <= k_incl) {
+                    v.a = (uint32_t)((w0 >> 31) & 0x7FFFFFFFu);
+                    v.b = (uint32_t)(w0 & 0x7FFFFFFFu);
+                    v.s = (uint32_t)w1;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    Tup y;
+                    y.a = __shfl_xor_sync(0xffffffffu, v.a, o);
+                    y.b = __shfl_xor_sync(0xffffffffu, v.b, o);
+                    y.s = __shfl_xor_sync(0xffffffffu, v.s, o);
+                    v = tup_comb(v, y);
+                }
+                excl = tup_comb(excl, v);
+                if (k_incl < 32) break;
+                basep -= 32;
+            }
+            if (lane == 0) {
+                if (aborted) {
+                    Tup z = {0, 0, 0};
+                    rr_publish(tile_state, tile_id, 3u, z);
+                    atomicExch(&scalars[2], 1u);
+                    s_abort = 1;
+                } else {
+                    rr_publish(tile_state, tile_id, 2u, tup_comb(excl, total));
+                }
+            }
+        }
+        if (lane == 0) {
+            s_excl = excl;
+            if (base + RR_TILE >= n_active) scalars[0] = excl.s + total.s;   // last tile: next active count
+        }
+    }
+    __syncthreads();
+    if (s_abort) return;
+    run = tup_comb(s_excl, run);
 
 #pragma unroll
     for (int e = 0; e < RR_IPT; ++e) {
@@ -330,18 +431,18 @@ rerank_apply_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
         // New rank of the suffix (1-based; 0 is "past the end"): the group's rank, or the
         // suffix's final SA slot if it is alone in its group.
         const uint32_t rank1 = ((f & 4u) ? ng : p) + 1;
-        if (f & 4u) {
-            const uint32_t c = run.s++;
-            out_idx[c] = idx[e];
-            out_grp[c] = ng;
-        } else {
-            sa[p] = (int32_t)idx[e];
-        }
+        if (!(f & 4u)) sa[p] = (int32_t)idx[e];
         if (pairs_out) {
-            // large rounds: the scatter into ISA is done later, partitioned by index window
-            pairs_out[k] = ((uint64_t)idx[e] << 32) | rank1;
-        } else if (first || rank1 != g + 1) {
-            isa[idx[e]] = rank1;
+            // large rounds: the scatter into ISA and the extraction of the next active set
+            // happen later, partitioned by index window; bit 31 marks "still active"
+            pairs_out[k] = ((uint64_t)idx[e] << 32) | rank1 | ((f & 4u) ? 0x80000000u : 0u);
+        } else {
+            if (f & 4u) {
+                const uint32_t c = run.s++;
+                out_idx[c] = idx[e];
+                out_grp[c] = ng;
+            }
+            if (first || rank1 != g + 1) isa[idx[e]] = rank1;
         }
     }
 }
@@ -391,7 +492,7 @@ int SaBuilder::ensure(int64_t n) {
     PSS_CUDA_TRY(cudaMalloc(&vals_b_, cap * sizeof(uint32_t)));
     PSS_CUDA_TRY(cudaMalloc(&grp_, cap * sizeof(uint32_t)));
     PSS_CUDA_TRY(cudaMalloc(&isa_, cap * sizeof(uint32_t)));
-    PSS_CUDA_TRY(cudaMalloc(&tile_aggr_, (size_t)div_up(cap, RR_TILE) * 3 * sizeof(uint32_t)));
+    PSS_CUDA_TRY(cudaMalloc(&tile_aggr_, (size_t)div_up(cap, RR_TILE) * 2 * sizeof(unsigned long long)));
     PSS_TRY(sorter_.ensure(cap));
     cap_ = cap;
     return PSS_OK;
@@ -476,9 +577,13 @@ int SaBuilder::build_device(const uint8_t *d_text, int32_t n, int32_t *d_sa, cud
     PSS_CUDA_TRY(cudaMemcpyAsync(d_small_ + SM_LUT, h_small_ + SM_LUT, 512, cudaMemcpyHostToDevice, s));
 
     // ---- round 0: packed-prefix keys, sort, rank ---------------------------------------
-    keygen_kernel<<<(unsigned)div_up(n, KG_TILE), KG_THREADS, 0, s>>>(
-        d_text, un, reinterpret_cast<const uint16_t *>(d_small_ + SM_LUT), b, m, keys_a_);
-    PSS_LAUNCH_CHECK();
+    PSS_TRY(sorter_.hist_reset(s));
+    {
+        const int grid = (int)std::min<int64_t>(div_up(n, KG_TILE), (int64_t)sorter_.num_sms() * 4);
+        keygen_kernel<<<grid, KG_THREADS, 0, s>>>(d_text, un, reinterpret_cast<const uint16_t *>(d_small_ + SM_LUT), b, m,
+                                                  keys_a_, hist_layout(0, m * b), sorter_.d_hist());
+        PSS_LAUNCH_CHECK();
+    }
 
     SortProfile prof;
     prof.timed = profiling_;
@@ -500,7 +605,8 @@ int SaBuilder::build_device(const uint8_t *d_text, int32_t n, int32_t *d_sa, cud
     const int gbits = bit_width_u64((uint64_t)un - 1);   // group ranks 0..n-1
     bool in_alt = false;
     stats_.active_per_round[0] = n;
-    PSS_TRY(sorter_.sort(keys_a_, keys_b_, vals_a_, vals_b_, un, 0, m * b, /*iota=*/true, s, &in_alt, &prof));
+    PSS_TRY(sorter_.sort(keys_a_, keys_b_, vals_a_, vals_b_, un, 0, m * b, /*iota=*/true, s, &in_alt, &prof,
+                         /*hist_done=*/true));
     record_passes(0, un);
 
     uint32_t partition_min = 1u << 22;
@@ -511,30 +617,31 @@ int SaBuilder::build_device(const uint8_t *d_text, int32_t n, int32_t *d_sa, cud
     uint64_t *k_sorted = in_alt ? keys_b_ : keys_a_;
     auto rerank = [&](bool first) -> int {
         const uint32_t tiles = (uint32_t)div_up(n_active, RR_TILE);
-        rerank_reduce_kernel<<<tiles, RR_THREADS, 0, s>>>(k_sorted, n_active, rbits, first ? 1 : 0, tile_aggr_);
-        PSS_LAUNCH_CHECK();
-        rerank_scan_kernel<<<1, RS_THREADS, 0, s>>>(tile_aggr_, tiles, d_small_ + SM_SCALARS);
-        PSS_LAUNCH_CHECK();
+        PSS_CUDA_TRY(cudaMemsetAsync(tile_aggr_, 0, (size_t)tiles * 2 * sizeof(unsigned long long), s));
+        PSS_CUDA_TRY(cudaMemsetAsync(d_small_ + SM_SCALARS, 0, 8 * sizeof(uint32_t), s));
         // Above the threshold the rank scatter is partitioned (pairs → one keys-only onesweep
         // pass on the index's top 8 bits → windowed scatter); below it the direct scatter
         // is cheaper than the extra launches.
         const bool partitioned = n_active >= partition_min;
         uint64_t *k_other = (k_sorted == keys_a_) ? keys_b_ : keys_a_;
         rerank_apply_kernel<<<tiles, RR_THREADS, 0, s>>>(k_sorted, v_sorted, n_active, rbits, first ? 1 : 0,
-                                                         tile_aggr_, isa_, partitioned ? k_other : nullptr, d_sa,
-                                                         v_free, grp_);
+                                                         reinterpret_cast<unsigned long long *>(tile_aggr_),
+                                                         d_small_ + SM_SCALARS, isa_, partitioned ? k_other : nullptr,
+                                                         d_sa, v_free, grp_);
         PSS_LAUNCH_CHECK();
         if (partitioned) {
             bool alt = false;
             const int ibits = bit_width_u64((uint64_t)un - 1);
             const int shift = 32 + std::max(0, ibits - RADIX_BITS);
             PSS_TRY(sorter_.partition(k_other, k_sorted, n_active, shift, (uint32_t)(RADIX - 1), s, &alt));
-            isa_scatter_kernel<<<(unsigned)div_up(n_active, 256 * 4), 256, 0, s>>>(alt ? k_sorted : k_other, n_active, isa_);
+            isa_scatter_kernel<<<(unsigned)div_up(n_active, 256 * 4), 256, 0, s>>>(
+                alt ? k_sorted : k_other, n_active, isa_, v_free, grp_, d_small_ + SM_SCALARS + 3);
             PSS_LAUNCH_CHECK();
         }
-        PSS_CUDA_TRY(cudaMemcpyAsync(h_small_ + SM_SCALARS, d_small_ + SM_SCALARS, sizeof(uint32_t),
+        PSS_CUDA_TRY(cudaMemcpyAsync(h_small_ + SM_SCALARS, d_small_ + SM_SCALARS, 4 * sizeof(uint32_t),
                                      cudaMemcpyDeviceToHost, s));
         PSS_CUDA_TRY(cudaStreamSynchronize(s));
+        if (h_small_[SM_SCALARS + 2]) return fail(PSS_ERR_CUDA, "re-rank: look-back watchdog fired");
         if (partitioned) PSS_TRY(sorter_.poll_error(s));
         n_active = h_small_[SM_SCALARS];
         return PSS_OK;
@@ -550,11 +657,15 @@ int SaBuilder::build_device(const uint8_t *d_text, int32_t n, int32_t *d_sa, cud
         stats_.active_per_round[round] = n_active;
         uint32_t *v_in = v_free;  // compacted active suffix indices written by the last re-rank
         uint32_t *v_alt = (v_in == vals_a_) ? vals_b_ : vals_a_;
-        gather_kernel<<<(unsigned)div_up(n_active, 256 * 4), 256, 0, s>>>(v_in, grp_, isa_, un, (uint32_t)std::min<uint64_t>(h, un),
-                                                                         rbits, n_active, keys_a_);
-        PSS_LAUNCH_CHECK();
+        PSS_TRY(sorter_.hist_reset(s));
+        {
+            const int grid = (int)std::min<int64_t>(div_up(n_active, 256 * 4), (int64_t)sorter_.num_sms() * 8);
+            gather_kernel<<<grid, 256, 0, s>>>(v_in, grp_, isa_, un, (uint32_t)std::min<uint64_t>(h, un), rbits, n_active,
+                                               keys_a_, hist_layout(0, rbits + gbits), sorter_.d_hist());
+            PSS_LAUNCH_CHECK();
+        }
         PSS_TRY(sorter_.sort(keys_a_, keys_b_, v_in, v_alt, n_active, 0, rbits + gbits, /*iota=*/false, s, &in_alt,
-                             &prof));
+                             &prof, /*hist_done=*/true));
         record_passes(round, n_active);
         k_sorted = in_alt ? keys_b_ : keys_a_;
         v_sorted = in_alt ? v_alt : v_in;
