@@ -304,7 +304,13 @@ def run_ours(args):
         pss.check(lib.pss_sa_builder_build_host(builder, h_text.data_ptr(), n, h_sa.data_ptr()))
 
     def e2e_search():
-        return reader.search_batch(pats)
+        """The C-ABI host call itself: host patterns in, host result tuples out (then freed)."""
+        res = C.c_void_p()
+        pss.check(lib.pss_reader_search_batch(reader.h, blob.ctypes.data, offs.ctypes.data, len(pats), C.byref(res)))
+        r = C.cast(res, C.POINTER(pss.Result)).contents
+        out = (int(r.n_entries), dict(ms_bounds=r.ms_bounds, ms_extract=r.ms_extract, ms_dedup=r.ms_dedup, ms_total=r.ms_total))
+        lib.pss_result_free(res)
+        return out
 
     for _ in range(min(W, 2)):
         e2e_build()
@@ -315,7 +321,7 @@ def run_ours(args):
         a = time.perf_counter()
         e2e_build()
         b = time.perf_counter()
-        qo, ch, st, en, sstats = e2e_search()
+        n_e2e_entries, sstats = e2e_search()
         c = time.perf_counter()
         eb += b - a
         es += c - b
@@ -323,7 +329,7 @@ def run_ours(args):
     e2e_build_s = max_over_ranks(eb / K)
     e2e_search_s = max_over_ranks(es / K)
     h2d_search = int(blob.nbytes + offs.nbytes)
-    d2h_search = int(len(ch) * 12 + len(pats) * 4)
+    d2h_search = int(n_e2e_entries * 12 + len(pats) * 4)
 
     # ---- Python boundary (list[str]) — one measurement, rank 0 ---------------------------------
     py_qps = None
@@ -335,7 +341,7 @@ def run_ours(args):
         t0 = time.perf_counter()
         res = py_reader.search_multiple(substrings=str_pats)
         py_qps = len(str_pats) / (time.perf_counter() - t0)
-        assert len(res) == len(ch)
+        assert len(res) == n_e2e_entries
         del res, py_reader
         tmpdir.cleanup()
 

@@ -115,7 +115,7 @@ private:
     int       device_        = -1;
     int       num_sms_       = 0;
     int       cfg_           = 0;     // index into the compiled tile geometries (PSS_PASS_CFG)
-    int       tile_items_    = 4096;  // records per tile of the selected geometry
+    int       tile_items_    = 4608;  // records per tile of the selected geometry
     int       ballot_mode_   = 2;     // ranking variant: 0 MATCH.ANY, 1 ballots, 2 chosen per pass (PSS_BALLOT)
     uint32_t  spread_threshold_ = 8000;   // MATCH.ANY only when a warp sees at most ~8 distinct digits
     int64_t   tile_capacity_ = 0;
