@@ -47,6 +47,29 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE line (the JSON).  Libraries (NCCL prints its version banner to
+# stdout) must not pollute it: fd 1 is pointed at stderr for the whole run and the JSON line
+# is written to the saved descriptor at the end.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 # --------------------------------------------------------------------------------------
 # clocks
 # --------------------------------------------------------------------------------------
@@ -136,6 +159,16 @@ def cpu_reference_run(steps, warmup, sample_bytes=CPU_SAMPLE, nq=N_QUERIES):
     }
 
 
+def workload_config(n, nq, world):
+    return {
+        "workload": "BASELINE configs[0]+[1]: %d-byte newline-delimited ASCII chunk per GPU (tools/synth.config1_text), "
+                    "SA build + search_multiple of %d substrings (len 4-32) over it" % (n, nq),
+        "chunk_bytes": n, "chunks": world, "queries": nq,
+        "l2_policy": "inputs larger than L2 (text %d MB, SA %d MB, sort buffers %d GB)" % (n >> 20, (4 * n) >> 20, (24 * n) >> 30),
+        "parallelism": "chunk-per-GPU x%d" % world,
+    }
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -145,14 +178,15 @@ def run_reference(args):
         "impl": "reference", "metric": "index_build_GBps", "value": r["build_GBps"], "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": (r["build_s"] + r["search_s"]) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32", "data": "synthetic",
-        "config": {"workload": "config1+2 sample: libsais on %d bytes + %d-query search_multiple, CPU" % (CPU_SAMPLE, N_QUERIES)},
+        "config": dict(workload_config(args.size, args.queries, max(args.gpus, 1)),
+                       reference_sample="each step = the reference CPU path on the first %d bytes of that chunk" % CPU_SAMPLE),
         "cpu_baseline": {"value": r["build_GBps"], "unit": "GB/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["build_GBps"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "search": {"metric": "search_multiple_qps", "value": r["search_qps"], "unit": "queries/s",
                    "e2e": {"value": r["search_qps"], "unit": "queries/s"}},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -170,7 +204,10 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a collective that cannot complete must fail in minutes, not hold N GPUs for the default 10
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=180))
     torch.cuda.set_device(local_rank)
     pss.check(pss.lib.pss_set_device(local_rank))
     dev = torch.device("cuda", local_rank)
@@ -222,6 +259,13 @@ def run_ours(args):
         tmpdir.cleanup()
     d_blob = torch.from_numpy(blob).to(dev)
     d_offs = torch.from_numpy(offs).to(dev)
+    if world > 1:
+        # rank 0's batch is THE query batch: agree on its size once, so that the per-step
+        # broadcasts below have identical shapes on every rank
+        d_blob, d_offs = D.broadcast_queries(d_blob if rank == 0 else None, d_offs if rank == 0 else None, dev, src=0)
+        offs = d_offs.cpu().numpy()
+        blob = d_blob.cpu().numpy()
+        pats = [bytes(blob[offs[i]:offs[i + 1]]) for i in range(len(offs) - 1)]
     cap = 1 << 22
     outs = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(4)]
 
@@ -374,13 +418,7 @@ def run_ours(args):
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": step_s * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 text / u32 ranks / u64 keys",
         "data": "synthetic",
-        "config": {
-            "workload": "BASELINE configs[0]+[1]: %d-byte newline-delimited ASCII chunk per GPU (tools/synth.config1_text), "
-                        "SA build + search_multiple of %d substrings (len 4-32) over it" % (n, len(pats)),
-            "chunk_bytes": n, "chunks": world, "queries": len(pats),
-            "l2_policy": "inputs larger than L2 (text %d MB, SA %d MB, sort buffers %d GB)" % (n >> 20, (4 * n) >> 20, (24 * n) >> 30),
-            "parallelism": "chunk-per-GPU x%d" % world,
-        },
+        "config": workload_config(n, len(pats), world),
         "build": {"device_event_ms": dev_build_s * 1e3, "host_call_ms": build_s * 1e3, "rounds": rounds,
                   "radix_passes": passes, "active_per_round": active, "h0_symbols": stats.h0,
                   "bits_per_symbol": stats.bits_per_symbol},
@@ -406,7 +444,7 @@ def run_ours(args):
     if cpu:
         line["cpu_baseline"] = {"value": cpu["build_GBps"], "unit": "GB/s", "cores": cpu["cores"], "kind": cpu["kind"],
                                 "sample": cpu["sample"], "search_qps": cpu["search_qps"]}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -421,6 +459,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-python", action="store_true")
     args = ap.parse_args()
+    capture_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -26,7 +26,7 @@ def broadcast_queries(blob, offsets, device, src=0):
     dist.broadcast(meta, src)
     nb, no = int(meta[0]), int(meta[1])
     if rank == src:
-        blob, offsets = blob.to(device), offsets.to(device)
+        blob, offsets = blob.to(device).contiguous(), offsets.to(device).contiguous()
     else:
         blob = torch.empty(nb, dtype=torch.uint8, device=device)
         offsets = torch.empty(no, dtype=torch.int64, device=device)
