@@ -11,9 +11,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -97,8 +100,26 @@ struct pss_writer {
     std::vector<uint8_t> text;   // the chunk being accumulated (size() == bytes buffered)
     size_t capacity = 0;         // logical Vec<u8> capacity the flush rule compares against
     std::unique_ptr<SaBuilder> builder;
-    Pinned sa_stage;
-    std::vector<int32_t> sa_small;
+
+    // In-order background serialiser: dump_data() hands a finished chunk (text + suffix
+    // array) to this thread and returns, so ingestion of chunk k+1 overlaps the multi-GB
+    // file write of chunk k.  Two pinned SA buffers ping-pong; records are written strictly
+    // in chunk order by the single thread, so the container is byte-identical to the
+    // reference's synchronous writer (lib.rs:112-119) and is valid after every completed record.
+    struct Job {
+        std::vector<uint8_t> text;
+        std::vector<int32_t> sa_small;   // suffix array of a small chunk (owned by the job)
+        int stage = -1;                  // or: index of the pinned buffer holding it
+    };
+    Pinned sa_stage[2];
+    bool   stage_busy[2] = {false, false};
+    std::deque<Job> queue;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::thread io_thread;
+    bool io_started = false, io_stop = false, io_active = false;
+    int  io_status = PSS_OK;
+    std::string io_error;
 
     // Rust's Vec::reserve on the logical capacity (RawVec::grow_amortized): the reference
     // flushes on `len + entry + 1 > capacity()` (lib.rs:75, :96), and an entry that exactly
@@ -115,39 +136,123 @@ struct pss_writer {
         reserve_logical(1);
         text.push_back('\n');
     }
+
+    void io_main() {
+        std::unique_lock<std::mutex> lock(mu);
+        while (true) {
+            cv.wait(lock, [&] { return io_stop || !queue.empty(); });
+            if (queue.empty()) break;   // io_stop and nothing left
+            Job job = std::move(queue.front());
+            queue.pop_front();
+            io_active = true;
+            lock.unlock();
+            const size_t n = job.text.size();
+            const int32_t *sa = job.stage >= 0 ? static_cast<const int32_t *>(sa_stage[job.stage].p) : job.sa_small.data();
+            const uint32_t n32 = (uint32_t)n, sab = (uint32_t)(n * 4);
+            bool ok = io_status == PSS_OK;
+            int err = 0;
+            if (ok) {
+                ok = std::fwrite(&n32, 4, 1, file) == 1 && std::fwrite(job.text.data(), 1, n, file) == n &&
+                     std::fwrite(&sab, 4, 1, file) == 1 && std::fwrite(sa, 4, n, file) == n;
+                err = errno;
+            }
+            lock.lock();
+            if (!ok && io_status == PSS_OK) {
+                io_status = PSS_ERR_IO;
+                io_error  = std::string("write to index file: ") + std::strerror(err);
+            }
+            if (job.stage >= 0) stage_busy[job.stage] = false;
+            io_active = false;
+            cv.notify_all();
+        }
+    }
+    // Status of the background writes so far (call with `mu` NOT held).
+    int check_io() {
+        std::lock_guard<std::mutex> lock(mu);
+        if (io_status != PSS_OK) return fail(io_status, io_error);
+        return PSS_OK;
+    }
+    // Wait until everything queued has reached the FILE buffer.
+    int drain() {
+        std::unique_lock<std::mutex> lock(mu);
+        cv.wait(lock, [&] { return queue.empty() && !io_active; });
+        if (io_status != PSS_OK) return fail(io_status, io_error);
+        return PSS_OK;
+    }
+    void stop_io() {
+        if (!io_started) return;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            io_stop = true;
+        }
+        cv.notify_all();
+        io_thread.join();
+        io_started = false;
+    }
 };
 
 static int writer_dump(pss_writer *w) {
     const size_t n = w->text.size();
     if (n == 0) return PSS_OK;
     if (n >= (1ull << 30)) return fail(PSS_ERR_ARG, "chunk of 2^30 bytes or more: the container's u32 length fields would wrap");
+    PSS_TRY(w->check_io());
     if (!w->builder) {
         w->builder.reset(new (std::nothrow) SaBuilder());
         if (!w->builder) return fail(PSS_ERR_NOMEM, "out of host memory");
         int rc = w->builder->init(-1, 0);
         if (rc != PSS_OK) { w->builder.reset(); return rc; }
     }
+    pss_writer::Job job;
     // SA lands in pinned memory for large chunks (full-rate D2H), in a plain vector otherwise.
     int32_t *sa = nullptr;
     if (n >= (1u << 20)) {
-        PSS_TRY(w->sa_stage.ensure(n * sizeof(int32_t)));
-        sa = static_cast<int32_t *>(w->sa_stage.p);
+        std::unique_lock<std::mutex> lock(w->mu);
+        w->cv.wait(lock, [&] { return !w->stage_busy[0] || !w->stage_busy[1]; });
+        job.stage = w->stage_busy[0] ? 1 : 0;
+        w->stage_busy[job.stage] = true;
+        lock.unlock();
+        int rc = w->sa_stage[job.stage].ensure(n * sizeof(int32_t));
+        if (rc != PSS_OK) {
+            std::lock_guard<std::mutex> relock(w->mu);
+            w->stage_busy[job.stage] = false;
+            return rc;
+        }
+        sa = static_cast<int32_t *>(w->sa_stage[job.stage].p);
     } else {
-        w->sa_small.resize(n);
-        sa = w->sa_small.data();
+        job.sa_small.resize(n);
+        sa = job.sa_small.data();
     }
-    PSS_TRY(w->builder->build_host(w->text.data(), (int32_t)n, sa));
-
-    const uint32_t n32 = (uint32_t)n, sab = (uint32_t)(n * 4);
-    if (std::fwrite(&n32, 4, 1, w->file) != 1 || std::fwrite(w->text.data(), 1, n, w->file) != n ||
-        std::fwrite(&sab, 4, 1, w->file) != 1 || std::fwrite(sa, 4, n, w->file) != n)
-        return io_fail("write to index file", nullptr);
-    w->text.clear();
+    int rc = w->builder->build_host(w->text.data(), (int32_t)n, sa);
+    if (rc != PSS_OK) {
+        if (job.stage >= 0) {
+            std::lock_guard<std::mutex> relock(w->mu);
+            w->stage_busy[job.stage] = false;
+            w->cv.notify_all();
+        }
+        return rc;
+    }
+    job.text.swap(w->text);   // the accumulator starts the next chunk empty
+    if (!w->io_started) {
+        try {
+            w->io_thread = std::thread([w] { w->io_main(); });
+        } catch (...) {
+            w->text.swap(job.text);
+            if (job.stage >= 0) w->stage_busy[job.stage] = false;
+            return fail(PSS_ERR_NOMEM, "cannot start the index writer thread");
+        }
+        w->io_started = true;
+    }
+    {
+        std::lock_guard<std::mutex> lock(w->mu);
+        w->queue.push_back(std::move(job));
+    }
+    w->cv.notify_all();
     return PSS_OK;
 }
 
 static int writer_finalize(pss_writer *w) {
     if (!w->text.empty()) PSS_TRY(writer_dump(w));
+    PSS_TRY(w->drain());
     if (std::fflush(w->file) != 0) return io_fail("flush index file", nullptr);
     return PSS_OK;
 }
@@ -226,6 +331,7 @@ int32_t pss_writer_finalize(pss_writer *w) {
 int32_t pss_writer_close(pss_writer *w) {
     if (!w) return PSS_OK;
     int rc = writer_finalize(w);
+    w->stop_io();
     if (std::fclose(w->file) != 0 && rc == PSS_OK) rc = io_fail("close index file", nullptr);
     delete w;
     return rc;

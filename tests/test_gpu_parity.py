@@ -253,6 +253,23 @@ def test_search_binary_text_and_long_lines(pss, oracle):
         o.close()
 
 
+def test_single_query_paths_small_and_overflow(pss, oracle):
+    """A one-query batch takes the fused single-launch path up to 8192 matching suffixes and
+    falls back to the general pipeline above that; both must agree with the oracle."""
+    text = synth.zipf_words_text(2_000_000, seed=61, vocab=1024, block=1 << 16)
+    entries = bytes(text).split(b"\n")[:-1]
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "s.idx")
+        _write(oracle.Writer, p, entries, 1 << 20)          # 2 chunks → 2 pairs per query
+        r, o = pss.Reader(p), oracle.Reader(p)
+        for pat in [b"zzzzzzzz", bytes(text[777:800]), bytes(text[5000:5006]), b"e", b" ", b"", b"\n", b"ab"]:
+            stats = _compare_searches(r, o, [pat])
+        # a few queries at once still fit the small path (<= 64 pairs)
+        _compare_searches(r, o, [bytes(text[k:k + 9]) for k in range(100, 3000, 100)])
+        r.close()
+        o.close()
+
+
 def test_empty_index_and_no_hits(pss, oracle):
     with tempfile.TemporaryDirectory() as d:
         p = os.path.join(d, "e.idx")
