@@ -412,6 +412,10 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     achieved = pass_bytes / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else 0.0
+    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
+    # (profiles/r01_ncu_pass_kernel_final.txt): 4.699 GB for 4.606 GB algorithmic → 1.02x
+    NCU_TRAFFIC_RATIO = 4.699 / 4.606
+    avg_alg_bytes = pass_bytes / n_pass_launch if n_pass_launch else 0.0
     total_bytes = n * world
     line = {
         "metric": "index_build_GBps", "value": total_bytes / build_s / 1e9, "unit": "GB/s",
@@ -434,7 +438,10 @@ def run_ours(args):
             "python_boundary_qps": py_qps,
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                     "traffic": None, "kernel": "onesweep_pass_kernel", "peak_source": peak_kind,
+                     "traffic": avg_alg_bytes * NCU_TRAFFIC_RATIO / 1e9 if n_pass_launch else None,
+                     "traffic_unit": "GB per launch (ncu dram read+write = 1.02x algorithmic, profiles/r01_ncu_pass_kernel_final.txt)",
+                     "algorithmic_GB_per_launch": avg_alg_bytes / 1e9,
+                     "kernel": "onesweep_pass_kernel", "peak_source": peak_kind,
                      "algorithmic_bytes": "24 B per record per pass (8 B key + 4 B value, read once + written once)",
                      "launches_timed": n_pass_launch, "avg_launch_ms": pass_ms / n_pass_launch if n_pass_launch else None,
                      "share_of_build": (pass_ms / K) / (dev_build_s * 1e3) if dev_build_s else None},
