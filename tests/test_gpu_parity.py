@@ -172,6 +172,31 @@ def test_writer_multichunk_vs_oracle(pss, oracle):
         assert open(a, "rb").read() == open(b, "rb").read()
 
 
+def test_writer_overlong_file_line_grows_capacity(pss, oracle):
+    """add_entries_from_file_lines has no "too big" check (lib.rs:73-79): a line longer than
+    max_chunk_len grows the buffer for good, which moves every later chunk boundary."""
+    rng = np.random.default_rng(5)
+    lines = [bytes(rng.integers(97, 123, size=int(k), dtype=np.uint8)) for k in
+             [10, 20, 3000, 15, 15, 900, 40, 40, 40, 7000, 5, 5, 5, 5, 5, 5, 5, 5]]
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "in.txt")
+        open(src, "wb").write(b"\n".join(lines) + b"\n")
+        for mcl in (64, 1000, 8):
+            a, b = os.path.join(d, "a.idx"), os.path.join(d, "b.idx")
+            w = pss.Writer(a, mcl)
+            assert w.add_entries_from_file_lines(src) == 0
+            assert w.add_entry("tail") in (0, -6)
+            w.close()
+            ow = oracle.Writer(b, mcl)
+            ow.add_entries_from_file_lines(src)
+            try:
+                ow.add_entry("tail")
+            except ValueError:
+                pass
+            ow.close()
+            assert open(a, "rb").read() == open(b, "rb").read(), mcl
+
+
 def test_writer_capacity_quirks(pss, oracle):
     """An entry that exactly fills the chunk doubles the capacity for good (Vec growth)."""
     with tempfile.TemporaryDirectory() as d:
