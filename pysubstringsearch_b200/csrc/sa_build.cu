@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 
 namespace pss {
 
@@ -517,6 +518,12 @@ void SaBuilder::release() {
     cudaFree(grp_); cudaFree(isa_); cudaFree(tile_aggr_); cudaFree(d_small_);
     cudaFree(d_text_); cudaFree(d_sa_);
     if (h_small_) cudaFreeHost(h_small_);
+    for (int i = 0; i < 2; ++i) {
+        if (stage_[i]) cudaFreeHost(stage_[i]);
+        if (stage_ev_[i]) cudaEventDestroy(stage_ev_[i]);
+        stage_[i] = nullptr;
+        stage_ev_[i] = nullptr;
+    }
     if (ev_begin_) cudaEventDestroy(ev_begin_);
     if (ev_end_) cudaEventDestroy(ev_end_);
     if (stream_) cudaStreamDestroy(stream_);
@@ -683,15 +690,104 @@ int SaBuilder::build_device(const uint8_t *d_text, int32_t n, int32_t *d_sa, cud
     return PSS_OK;
 }
 
+// ---- host <-> device copies for callers with ordinary (pageable) memory -----------------------
+// A Rust/C host calls pss_libsais with plain heap buffers.  cudaMemcpy from/to pageable memory
+// runs at a fraction of the PCIe rate (one driver thread stages through a small pinned
+// buffer), and the 4n-byte suffix array is four times the text.  These helpers stage through
+// two pinned slices themselves and move the slices with several CPU threads while the DMA of
+// the next slice is in flight.
+namespace {
+
+constexpr size_t STAGE_SLICE = 16u << 20;
+constexpr size_t STAGE_MIN   = 8u << 20;   // below this a plain cudaMemcpy is as good
+
+bool host_pointer_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+void parallel_memcpy(uint8_t *dst, const uint8_t *src, size_t len, int threads) {
+    if (threads <= 1 || len < (1u << 20)) {
+        std::memcpy(dst, src, len);
+        return;
+    }
+    const size_t part = (len / threads + 4095) & ~(size_t)4095;
+    std::vector<std::thread> pool;
+    size_t off = 0;
+    for (int t = 0; t < threads - 1 && off + part < len; ++t, off += part)
+        pool.emplace_back([=] { std::memcpy(dst + off, src + off, part); });
+    std::memcpy(dst + off, src + off, len - off);
+    for (auto &th : pool) th.join();
+}
+
+int copy_threads() {
+    unsigned hc = std::thread::hardware_concurrency();
+    int t = hc ? (int)std::min<unsigned>(8, std::max<unsigned>(1, hc / 2)) : 4;
+    if (const char *e = std::getenv("PSS_COPY_THREADS")) t = std::max(1, std::atoi(e));
+    return t;
+}
+
+}  // namespace
+
+int SaBuilder::staged_copy(void *dst, const void *src, size_t bytes, bool to_device) {
+    if (!stage_[0]) {
+        for (int i = 0; i < 2; ++i) {
+            PSS_CUDA_TRY(cudaMallocHost(&stage_[i], STAGE_SLICE));
+            PSS_CUDA_TRY(cudaEventCreateWithFlags(&stage_ev_[i], cudaEventDisableTiming));
+        }
+    }
+    const int threads = copy_threads();
+    uint8_t *d = static_cast<uint8_t *>(dst);
+    const uint8_t *s = static_cast<const uint8_t *>(src);
+    const size_t nsl = (bytes + STAGE_SLICE - 1) / STAGE_SLICE;
+    auto len_of = [&](size_t i) { return std::min(STAGE_SLICE, bytes - i * STAGE_SLICE); };
+    if (to_device) {
+        for (size_t i = 0; i < nsl; ++i) {
+            const int b = (int)(i & 1);
+            if (i >= 2) PSS_CUDA_TRY(cudaEventSynchronize(stage_ev_[b]));   // slice i-2 has left the bounce buffer
+            parallel_memcpy(static_cast<uint8_t *>(stage_[b]), s + i * STAGE_SLICE, len_of(i), threads);
+            PSS_CUDA_TRY(cudaMemcpyAsync(d + i * STAGE_SLICE, stage_[b], len_of(i), cudaMemcpyHostToDevice, stream_));
+            PSS_CUDA_TRY(cudaEventRecord(stage_ev_[b], stream_));
+        }
+        return PSS_OK;   // completion is ordered on stream_
+    }
+    for (size_t i = 0; i <= nsl; ++i) {
+        if (i < nsl) {
+            const int b = (int)(i & 1);
+            PSS_CUDA_TRY(cudaMemcpyAsync(stage_[b], s + i * STAGE_SLICE, len_of(i), cudaMemcpyDeviceToHost, stream_));
+            PSS_CUDA_TRY(cudaEventRecord(stage_ev_[b], stream_));
+        }
+        if (i >= 1) {   // while slice i is in flight, move slice i-1 out of its bounce buffer
+            const int pb = (int)((i - 1) & 1);
+            PSS_CUDA_TRY(cudaEventSynchronize(stage_ev_[pb]));
+            parallel_memcpy(d + (i - 1) * STAGE_SLICE, static_cast<const uint8_t *>(stage_[pb]), len_of(i - 1), threads);
+        }
+    }
+    return PSS_OK;
+}
+
 int SaBuilder::build_host(const uint8_t *h_text, int32_t n, int32_t *h_sa) {
     if (n < 0 || (n > 0 && (!h_text || !h_sa))) return fail(PSS_ERR_ARG, "bad build arguments");
     if (n == 0) return PSS_OK;
     PSS_CUDA_TRY(cudaSetDevice(device_));
     PSS_TRY(ensure_io(n));
-    PSS_CUDA_TRY(cudaMemcpyAsync(d_text_, h_text, (size_t)n, cudaMemcpyHostToDevice, stream_));
+    const bool big = (size_t)n >= STAGE_MIN;
+    if (big && !host_pointer_is_pinned(h_text)) {
+        PSS_TRY(staged_copy(d_text_, h_text, (size_t)n, /*to_device=*/true));
+    } else {
+        PSS_CUDA_TRY(cudaMemcpyAsync(d_text_, h_text, (size_t)n, cudaMemcpyHostToDevice, stream_));
+    }
     PSS_TRY(build_device(d_text_, n, d_sa_, stream_));
-    PSS_CUDA_TRY(cudaMemcpyAsync(h_sa, d_sa_, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
-    PSS_CUDA_TRY(cudaStreamSynchronize(stream_));
+    if (big && !host_pointer_is_pinned(h_sa)) {
+        PSS_TRY(staged_copy(h_sa, d_sa_, (size_t)n * sizeof(int32_t), /*to_device=*/false));
+    } else {
+        PSS_CUDA_TRY(cudaMemcpyAsync(h_sa, d_sa_, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+        PSS_CUDA_TRY(cudaStreamSynchronize(stream_));
+    }
     return PSS_OK;
 }
 

@@ -46,6 +46,7 @@ public:
 
 private:
     int ensure(int64_t n);
+    int staged_copy(void *dst, const void *src, size_t bytes, bool to_device);
 
     int          device_   = -1;
     cudaStream_t stream_   = nullptr;
@@ -62,6 +63,8 @@ private:
     uint8_t     *d_text_   = nullptr;
     int32_t     *d_sa_     = nullptr;
     cudaEvent_t  ev_begin_ = nullptr, ev_end_ = nullptr;
+    void        *stage_[2]    = {nullptr, nullptr};   // pinned bounce slices for pageable callers
+    cudaEvent_t  stage_ev_[2] = {nullptr, nullptr};
     bool         profiling_ = false;
     pss_build_stats stats_ = {};
     std::vector<pss_pass_stat> pass_stats_;
