@@ -100,9 +100,10 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         sm, smax, reasons = [], [], set()
-        for t, line in self.lines:
-            if t0 is not None and not (t0 - 0.05 <= t <= t1 + 0.05):
-                continue
+        in_window = [x for x in self.lines if t0 is None or (t0 - 0.05 <= x[0] <= t1 + 0.05)]
+        # a timed region shorter than the sampling period can fall between two samples: then
+        # report the samples taken around it (the sampler starts 0.3 s before the region)
+        for t, line in (in_window or self.lines):
             p = [x.strip() for x in line.split(",")]
             if len(p) < 8:
                 continue
@@ -159,13 +160,18 @@ def cpu_reference_run(steps, warmup, sample_bytes=CPU_SAMPLE, nq=N_QUERIES):
     }
 
 
-def workload_config(n, nq, world):
+def workload_config(n, nq, world, n_chunks=0):
+    n_chunks = n_chunks or world
+    if n_chunks == world:
+        what = "BASELINE configs[0]+[1]: %d-byte newline-delimited ASCII chunk per GPU (tools/synth.config1_text), " \
+               "SA build + search_multiple of %d substrings (len 4-32) over it" % (n, nq)
+    else:
+        what = "BASELINE configs[2] shape: %d chunks x %d bytes (tools/synth.config1_text, seed per chunk) sharded " \
+               "chunk k -> rank k %% %d, full build + search_multiple of %d substrings" % (n_chunks, n, world, nq)
     return {
-        "workload": "BASELINE configs[0]+[1]: %d-byte newline-delimited ASCII chunk per GPU (tools/synth.config1_text), "
-                    "SA build + search_multiple of %d substrings (len 4-32) over it" % (n, nq),
-        "chunk_bytes": n, "chunks": world, "queries": nq,
+        "workload": what, "chunk_bytes": n, "chunks": n_chunks, "queries": nq,
         "l2_policy": "inputs larger than L2 (text %d MB, SA %d MB, sort buffers %d GB)" % (n >> 20, (4 * n) >> 20, (24 * n) >> 30),
-        "parallelism": "chunk-per-GPU x%d" % world,
+        "parallelism": "chunk k -> GPU k %% %d (%d chunk(s) on the busiest GPU)" % (world, -(-n_chunks // world)),
     }
 
 
@@ -178,7 +184,7 @@ def run_reference(args):
         "impl": "reference", "metric": "index_build_GBps", "value": r["build_GBps"], "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": (r["build_s"] + r["search_s"]) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32", "data": "synthetic",
-        "config": dict(workload_config(args.size, args.queries, max(args.gpus, 1)),
+        "config": dict(workload_config(args.size, args.queries, max(args.gpus, 1), args.chunks),
                        reference_sample="each step = the reference CPU path on the first %d bytes of that chunk" % CPU_SAMPLE),
         "cpu_baseline": {"value": r["build_GBps"], "unit": "GB/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["build_GBps"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -228,30 +234,35 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- inputs -----------------------------------------------------------------------
+    # ---- inputs: chunk k of the index belongs to rank k % world ---------------------------------
+    n_chunks = args.chunks if args.chunks > 0 else world
+    assert n_chunks >= world, "--chunks must be at least the number of ranks"
+    chunk_ids = [k for k in range(n_chunks) if D.chunk_owner(k, world) == rank]
     t_gen = time.perf_counter()
-    text = synth.config1_text(n, seed=20240501 + 1000 * rank)
+    texts = [synth.config1_text(n, seed=20240501 + 1000 * k) for k in chunk_ids]
+    text = texts[0]
     pats = synth.config2_queries(text, nq=args.queries, seed=7)     # same seed: rank 0's are used
     blob, offs = synth.pack_patterns(pats)
-    log("[rank %d] generated %d bytes + %d queries in %.1fs" % (rank, n, len(pats), time.perf_counter() - t_gen))
-    h_text = torch.from_numpy(text).pin_memory()
+    log("[rank %d] generated %d x %d bytes + %d queries in %.1fs" % (rank, len(texts), n, len(pats), time.perf_counter() - t_gen))
+    h_texts = [torch.from_numpy(t).pin_memory() for t in texts]
     h_sa = torch.empty(n, dtype=torch.int32).pin_memory()
-    d_text = h_text.to(dev)
+    d_texts = [h.to(dev) for h in h_texts]
     d_sa = torch.empty(n, dtype=torch.int32, device=dev)
     builder = C.c_void_p()
     pss.check(lib.pss_sa_builder_create(local_rank, n, C.byref(builder)))
     pss.check(lib.pss_sa_builder_set_profiling(builder, 1))
 
-    # ---- index for the SEARCH half: the real Writer → file → Reader path, once, untimed ---------
+    # ---- index for the SEARCH half: this rank's chunks in the reference container, once, untimed ----
     tmpdir = tempfile.TemporaryDirectory()
     path = os.path.join(tmpdir.name, "bench_rank%d.idx" % rank)
     t0 = time.perf_counter()
-    pss.check(lib.pss_sa_builder_build_host(builder, h_text.data_ptr(), n, h_sa.data_ptr()))
     with open(path, "wb") as f:                          # container layout of lib.rs:112-119
-        f.write(np.uint32(n).tobytes())
-        f.write(memoryview(text))
-        f.write(np.uint32(n * 4).tobytes())
-        f.write(memoryview(h_sa.numpy()))
+        for t, h in zip(texts, h_texts):
+            pss.check(lib.pss_sa_builder_build_host(builder, h.data_ptr(), n, h_sa.data_ptr()))
+            f.write(np.uint32(n).tobytes())
+            f.write(memoryview(t))
+            f.write(np.uint32(n * 4).tobytes())
+            f.write(memoryview(h_sa.numpy()))
     t1 = time.perf_counter()
     reader = pss.Reader(path)
     log("[rank %d] index written (%.1fs) and opened on the GPU (%.1fs)" % (rank, t1 - t0, time.perf_counter() - t1))
@@ -296,42 +307,52 @@ def run_ours(args):
                 k = sum(int(p.shape[1]) for p in parts)
         return k, n_hits.value
 
-    def build_device():
-        pss.check(lib.pss_sa_builder_build_device(builder, d_text.data_ptr(), n, d_sa.data_ptr(), None))
-
     stats = pss.BuildStats()
     pstats = (pss.PassStat * 512)()
+
+    def build_device(acc=None):
+        """Device-resident BUILD of every chunk this rank owns (text in HBM → SA in HBM)."""
+        for d_text in d_texts:
+            pss.check(lib.pss_sa_builder_build_device(builder, d_text.data_ptr(), n, d_sa.data_ptr(), None))
+            if acc is not None:
+                lib.pss_sa_builder_stats(builder, C.byref(stats), pstats)
+                acc["dev_ms"] += stats.total_ms
+                for i in range(stats.n_pass_stats):
+                    acc["pass_bytes"] += 24.0 * pstats[i].n_records
+                    acc["pass_ms"] += pstats[i].ms
+                    acc["launches"] += 1
 
     # ---- device-resident timed region -------------------------------------------------------
     idx = torch.cuda.current_device()
     for _ in range(W):
         build_device()
         search_device()
+    # rank 0 samples its own GPU's clocks; one nvidia-smi poller per rank would contend for the
+    # driver lock and add milliseconds to every small kernel launch / sync of the other ranks
     sampler = ClockSampler(idx)
-    sampler.start()
-    time.sleep(0.3)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
     launches0 = lib.pss_kernel_launch_count()
     barrier()
     t_begin = time.perf_counter()
     build_t = search_t = 0.0
-    dev_build_ms = 0.0
-    pass_bytes = pass_ms = 0.0
-    n_pass_launch = 0
+    acc = {"dev_ms": 0.0, "pass_bytes": 0.0, "pass_ms": 0.0, "launches": 0}
     entries = hits = 0
     for _ in range(K):
         a = time.perf_counter()
-        build_device()
+        build_device(acc)
         b = time.perf_counter()
+        # ranks may own different numbers of chunks (15 over 8): align them here, so that the
+        # wait for the busiest builder is not booked as search time by the idle ranks
+        if world > 1:
+            barrier()
+        b2 = time.perf_counter()
         entries, hits = search_device()
         c = time.perf_counter()
         build_t += b - a
-        search_t += c - b
-        lib.pss_sa_builder_stats(builder, C.byref(stats), pstats)
-        dev_build_ms += stats.total_ms
-        for i in range(stats.n_pass_stats):
-            pass_bytes += 24.0 * pstats[i].n_records
-            pass_ms += pstats[i].ms
-            n_pass_launch += 1
+        search_t += c - b2
+    dev_build_ms, pass_bytes, pass_ms, n_pass_launch = acc["dev_ms"], acc["pass_bytes"], acc["pass_ms"], acc["launches"]
     barrier()
     t_end = time.perf_counter()
     launches = lib.pss_kernel_launch_count() - launches0
@@ -345,7 +366,8 @@ def run_ours(args):
 
     # ---- end-to-end through the C-ABI host calls (pinned host buffers) ------------------------
     def e2e_build():
-        pss.check(lib.pss_sa_builder_build_host(builder, h_text.data_ptr(), n, h_sa.data_ptr()))
+        for h in h_texts:
+            pss.check(lib.pss_sa_builder_build_host(builder, h.data_ptr(), n, h_sa.data_ptr()))
 
     def e2e_search():
         """The C-ABI host call itself: host patterns in, host result tuples out (then freed)."""
@@ -378,8 +400,8 @@ def run_ours(args):
     t0 = time.perf_counter()
     pss.check(lib.pss_libsais(text.ctypes.data, sa_pageable.ctypes.data, n, 0, None))
     libsais_pageable_s = max_over_ranks(time.perf_counter() - t0)
-    sa_matches = bool(np.array_equal(sa_pageable[:1 << 20], h_sa.numpy()[:1 << 20]) and
-                      np.array_equal(sa_pageable[-(1 << 20):], h_sa.numpy()[-(1 << 20):]))
+    pss.check(lib.pss_sa_builder_build_host(builder, h_texts[0].data_ptr(), n, h_sa.data_ptr()))
+    sa_matches = bool(np.array_equal(sa_pageable, h_sa.numpy()))
     del sa_pageable
     h2d_search = int(blob.nbytes + offs.nbytes)
     d2h_search = int(n_e2e_entries * 12 + len(pats) * 4)
@@ -425,19 +447,19 @@ def run_ours(args):
     # (profiles/r01_ncu_pass_kernel_final.txt): 4.699 GB for 4.606 GB algorithmic → 1.02x
     NCU_TRAFFIC_RATIO = 4.699 / 4.606
     avg_alg_bytes = pass_bytes / n_pass_launch if n_pass_launch else 0.0
-    total_bytes = n * world
+    total_bytes = n * n_chunks
     line = {
         "metric": "index_build_GBps", "value": total_bytes / build_s / 1e9, "unit": "GB/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": step_s * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 text / u32 ranks / u64 keys",
-        "data": "synthetic",
-        "config": workload_config(n, len(pats), world),
+        "higher_is_better": True, "scaling": "weak" if n_chunks == world else "strong", "vs_baseline": None,
+        "dtype": "u8 text / u32 ranks / u64 keys", "data": "synthetic",
+        "config": workload_config(n, len(pats), world, n_chunks),
         "build": {"device_event_ms": dev_build_s * 1e3, "host_call_ms": build_s * 1e3, "rounds": rounds,
                   "radix_passes": passes, "active_per_round": active, "h0_symbols": stats.h0,
                   "bits_per_symbol": stats.bits_per_symbol},
         "e2e": {"value": total_bytes / e2e_build_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": 4 * n,
                 "ms_per_step": e2e_build_s * 1e3,
-                "pss_libsais_pageable": {"value": total_bytes / libsais_pageable_s / 1e9, "unit": "GB/s",
+                "pss_libsais_pageable": {"value": n * world / libsais_pageable_s / 1e9, "unit": "GB/s",
                                          "ms": libsais_pageable_s * 1e3, "same_sa_as_pinned_path": sa_matches}},
         "search": {
             "metric": "search_multiple_qps", "value": len(pats) / search_s, "unit": "queries/s",
@@ -474,6 +496,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=N_TEXT, help="chunk bytes per GPU (default: the 500 MB config)")
     ap.add_argument("--queries", type=int, default=N_QUERIES)
+    ap.add_argument("--chunks", type=int, default=0,
+                    help="total chunks of the index, sharded chunk k -> rank k %% N (default: one per GPU = weak scaling; "
+                         "15 with --size 536870912 is BASELINE configs[2])")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-python", action="store_true")
     args = ap.parse_args()
