@@ -40,7 +40,7 @@ from tools import synth  # noqa: E402
 
 N_TEXT = 500_000_000
 N_QUERIES = 10_000
-CPU_SAMPLE = 64 << 20
+CPU_SAMPLE = int(os.environ.get("PSS_BENCH_CPU_SAMPLE", 64 << 20))   # bytes of the chunk the CPU arm processes per step
 
 
 def log(*a):
@@ -179,7 +179,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    r = cpu_reference_run(args.steps, args.warmup)
+    r = cpu_reference_run(args.steps, args.warmup, nq=args.queries)
     line = {
         "impl": "reference", "metric": "index_build_GBps", "value": r["build_GBps"], "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": (r["build_s"] + r["search_s"]) * 1e3,
