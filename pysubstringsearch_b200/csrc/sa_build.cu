@@ -167,12 +167,20 @@ isa_scatter_kernel(const uint64_t *__restrict__ pairs, uint32_t n_pairs, uint32_
     const uint32_t base = (blockIdx.x * 256 + threadIdx.x) * U;
     uint64_t v[U];
     uint32_t kept = 0;
+    if (base + U <= n_pairs) {   // 4 pairs = 32 aligned bytes: two 16-byte loads
+        const uint4 *vp = reinterpret_cast<const uint4 *>(pairs + base);
+        const uint4 a = ld_stream_u128(vp), b = ld_stream_u128(vp + 1);
+        v[0] = ((uint64_t)a.y << 32) | a.x; v[1] = ((uint64_t)a.w << 32) | a.z;
+        v[2] = ((uint64_t)b.y << 32) | b.x; v[3] = ((uint64_t)b.w << 32) | b.z;
+    } else {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const uint32_t k = base + u;
-        v[u] = k < n_pairs ? ld_stream_u64(pairs + k) : 0ull;
-        kept += (uint32_t)(v[u] >> 31) & 1u;
+        for (int u = 0; u < U; ++u) {
+            const uint32_t k = base + u;
+            v[u] = k < n_pairs ? ld_stream_u64(pairs + k) : 0ull;
+        }
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u) kept += (uint32_t)(v[u] >> 31) & 1u;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const uint32_t k = base + u;
@@ -330,19 +338,29 @@ rerank_apply_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
     const uint32_t base    = tile_id * RR_TILE;
     rerank_load(tile, keys, base, n_active);
 
+    static_assert(RR_IPT == 8, "the vector loads/stores below move 8 records per thread");
     uint32_t flags[RR_IPT];
     uint32_t idx[RR_IPT];
+    const bool full_tile = base + RR_TILE <= n_active;
+    if (full_tile) {
+        // a thread's 8 suffix indices are 32 contiguous, 32-byte aligned bytes: two 16-byte loads
+        // instead of eight 4-byte ones that would each pull a whole sector for 4 useful bytes
+        const uint4 *vp = reinterpret_cast<const uint4 *>(vals + base + threadIdx.x * RR_IPT);
+        const uint4 a = ld_stream_u128(vp), b = ld_stream_u128(vp + 1);
+        idx[0] = a.x; idx[1] = a.y; idx[2] = a.z; idx[3] = a.w;
+        idx[4] = b.x; idx[5] = b.y; idx[6] = b.z; idx[7] = b.w;
+    }
     Tup agg = {0, 0, 0};
 #pragma unroll
     for (int e = 0; e < RR_IPT; ++e) {
         uint32_t loc = threadIdx.x * RR_IPT + e;
         uint32_t k   = base + loc;
         flags[e] = 0;
-        idx[e]   = 0;
+        if (!full_tile) idx[e] = 0;
         if (k < n_active) {
             uint32_t f = rerank_flags(tile, loc + 1, k, n_active, gs, first != 0);
             flags[e]   = f | 8u;  // bit3: record exists
-            idx[e]     = ld_stream_u32(vals + k);
+            if (!full_tile) idx[e] = ld_stream_u32(vals + k);
             if (f & 1u) agg.a = k + 1;
             if (f & 2u) agg.b = k + 1;
             agg.s += (f >> 2) & 1u;
@@ -417,8 +435,10 @@ rerank_apply_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
     if (s_abort) return;
     run = tup_comb(s_excl, run);
 
+    uint64_t pr[RR_IPT];
 #pragma unroll
     for (int e = 0; e < RR_IPT; ++e) {
+        pr[e] = 0;
         if (!(flags[e] & 8u)) continue;
         uint32_t loc = threadIdx.x * RR_IPT + e;
         uint32_t k   = base + loc;
@@ -436,7 +456,8 @@ rerank_apply_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
         if (pairs_out) {
             // large rounds: the scatter into ISA and the extraction of the next active set
             // happen later, partitioned by index window; bit 31 marks "still active"
-            pairs_out[k] = ((uint64_t)idx[e] << 32) | rank1 | ((f & 4u) ? 0x80000000u : 0u);
+            pr[e] = ((uint64_t)idx[e] << 32) | rank1 | ((f & 4u) ? 0x80000000u : 0u);
+            if (!full_tile) pairs_out[k] = pr[e];
         } else {
             if (f & 4u) {
                 const uint32_t c = run.s++;
@@ -445,6 +466,11 @@ rerank_apply_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
             }
             if (first || rank1 != g + 1) isa[idx[e]] = rank1;
         }
+    }
+    if (pairs_out && full_tile) {
+        ulonglong2 *pp = reinterpret_cast<ulonglong2 *>(pairs_out + base + threadIdx.x * RR_IPT);
+#pragma unroll
+        for (int j = 0; j < RR_IPT / 2; ++j) pp[j] = make_ulonglong2(pr[2 * j], pr[2 * j + 1]);
     }
 }
 
