@@ -417,3 +417,52 @@ def test_python_writer_drop_flushes(oracle):
         w.add_entry(text="never finalized")
         del w                                   # Drop → finalize (lib.rs:138-144)
         assert oracle.Reader(p).search("final") == ["never finalized"]
+
+
+# ------------------------------------------------------------------------------------
+# full size (BASELINE configs[0]: one 500 000 000-byte chunk) — size-independent properties
+# ------------------------------------------------------------------------------------
+def test_full_size_config1_properties(pss):
+    """The oracle is too slow at this size, so the 500 MB build is checked through properties
+    that pin a suffix array completely: SA is a permutation of 0..n-1, and for neighbours
+    SA[k-1], SA[k]: T[a] < T[b], or T[a] == T[b] and rank(a+1) < rank(b+1) (past-the-end = -1).
+    The searches are checked against an independent scan of the text."""
+    n = 500_000_000
+    text = synth.config1_text(n)
+    sa = pss.libsais(text)
+    seen = np.zeros(n, dtype=bool)
+    seen[sa] = True
+    assert seen.all(), "SA is not a permutation"
+    del seen
+    isa = np.empty(n, dtype=np.int32)
+    isa[sa] = np.arange(n, dtype=np.int32)
+    step = 50_000_000                       # bounded temporaries
+    for lo in range(1, n, step):
+        hi = min(n, lo + step)
+        a, b = sa[lo - 1:hi - 1], sa[lo:hi]
+        ta, tb = text[a], text[b]
+        ra = np.where(a + 1 < n, isa[np.minimum(a + 1, n - 1)], -1)
+        rb = np.where(b + 1 < n, isa[np.minimum(b + 1, n - 1)], -1)
+        assert bool(np.all((ta < tb) | ((ta == tb) & (ra < rb)))), "suffixes out of order in [%d, %d)" % (lo, hi)
+    del isa
+    # search on the same index: entries containing the pattern, found independently
+    raw = text.tobytes()
+    nl = np.flatnonzero(text == 10)
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "full.idx")
+        with open(p, "wb") as f:
+            f.write(np.uint32(n).tobytes()); f.write(memoryview(text))
+            f.write(np.uint32(4 * n).tobytes()); f.write(memoryview(sa))
+        r = pss.Reader(p)
+    for pat in (b"google", b"text_two", b"qqqqqqqqqq"):
+        hits, at = [], raw.find(pat)
+        while at >= 0:
+            hits.append(at)
+            at = raw.find(pat, at + 1)
+        lines = np.unique(np.searchsorted(nl, np.array(hits, dtype=np.int64), side="left")) if hits else np.zeros(0, np.int64)
+        want_start = np.where(lines > 0, nl[np.maximum(lines - 1, 0)] + 1, 0) if len(lines) else np.zeros(0, np.int64)
+        qo, ch, st, en, _ = r.search_batch([pat])
+        assert len(st) == len(lines)
+        assert np.array_equal(np.sort(st.astype(np.int64)), np.sort(want_start))
+        assert np.array_equal(np.sort(en.astype(np.int64)), np.sort(nl[lines])) if len(lines) else len(en) == 0
+    r.close()
