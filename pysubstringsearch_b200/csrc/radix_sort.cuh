@@ -2,7 +2,7 @@
 //
 // One upfront histogram kernel computes the 256-bin histograms of every 8-bit digit in
 // [begin_bit, end_bit); each digit then costs ONE pass over the data: a tile (CTA) ranks
-// its records with warp-level match_any, publishes its per-digit counts, resolves its
+// its records inside each warp (ballots or MATCH.ANY), publishes its per-digit counts, resolves its
 // global offsets by decoupled look-back over the preceding tiles, stages the records in
 // shared memory in digit order and writes them out in coalesced per-digit runs.
 // Digits whose histogram has a single non-empty bin are skipped on the host.

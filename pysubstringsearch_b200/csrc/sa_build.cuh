@@ -7,8 +7,10 @@
 //             codes, 0 = past the end, so a proper prefix sorts first without a sentinel),
 //             onesweep-sort (key, index), derive group ranks
 //   round r   for the suffixes still sharing a group: key = (group rank, rank of suffix
-//             i + h); onesweep-sort; segmented re-rank; settled suffixes are written to
-//             SA and leave the active set (Larsson–Sadakane style filtering); h doubles
+//             i + h); onesweep-sort; single-pass segmented re-rank; settled suffixes are
+//             written to SA and leave the active set (Larsson–Sadakane style filtering);
+//             ranks are scattered into ISA window by window after one partition pass;
+//             h doubles
 //
 // The suffix array of a text is unique, so the result is byte-identical to libsais'.
 #pragma once
@@ -57,8 +59,8 @@ private:
     uint32_t    *vals_a_   = nullptr, *vals_b_ = nullptr;
     uint32_t    *grp_      = nullptr;
     uint32_t    *isa_      = nullptr;
-    uint32_t    *tile_aggr_ = nullptr;   // 3 words per rerank tile
-    uint32_t    *d_small_  = nullptr;    // presence[8] | scalars[8] | lut[256 bytes]
+    uint32_t    *tile_aggr_ = nullptr;   // re-rank look-back state: two u64 words per 2048-record tile
+    uint32_t    *d_small_  = nullptr;    // presence[8] | scalars[8] | code LUT (256 x u16)
     uint32_t    *h_small_  = nullptr;    // pinned mirror
     uint8_t     *d_text_   = nullptr;
     int32_t     *d_sa_     = nullptr;
