@@ -468,6 +468,7 @@ int Searcher::init(int device) {
     PSS_CUDA_TRY(cudaMalloc(&d_scalar_, 16 * sizeof(uint32_t)));
     PSS_CUDA_TRY(cudaMallocHost(&h_scalar_, 16 * sizeof(uint32_t)));
     PSS_CUDA_TRY(cudaMalloc(&d_small_out_, SMALL_OUT_BYTES));
+    PSS_CUDA_TRY(cudaMemset(d_small_out_, 0, SMALL_OUT_BYTES));   // the whole block is copied back every call
     PSS_CUDA_TRY(cudaMallocHost(&h_small_out_, SMALL_OUT_BYTES));
     PSS_CUDA_TRY(cudaFuncSetAttribute(small_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(SmallSmem)));
@@ -680,6 +681,8 @@ int Searcher::search(const uint8_t *d_patterns, const int64_t *d_offsets, int32_
         uint32_t *o_s = nullptr, *o_e = nullptr;
         PSS_TRY(sink->reserve(kept, &o_q, &o_c, &o_s, &o_e));
         if (!o_s || !o_e) return fail(PSS_ERR_ARG, "search sink returned null output buffers");
+        if (per_pair_count)   // pairs without hits never get an entry: keep the copied-back array defined
+            PSS_CUDA_TRY(cudaMemsetAsync(d_pair_first_, 0, (size_t)np * sizeof(uint32_t), s));
         compact_kernel<<<tiles, CP_THREADS, 0, s>>>(d_flag_, d_end_, d_tile_sum_, d_hit_off_, d_chunks_, nc, a, np, nh,
                                                     d_pair_first_, o_q, o_c, o_s, o_e);
         PSS_LAUNCH_CHECK();
