@@ -142,3 +142,43 @@ def test_oracle_semantics(oracle):
         w.close()
         assert os.path.getsize(p) == 0
         assert oracle.Reader(p).search("a") == []
+
+
+def test_port_property_based(oracle):
+    """Hypothesis: for arbitrary short byte strings over a tiny alphabet (many ties, NUL and
+    0xFF included) the port equals the definition-level suffix sort."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.binary(min_size=0, max_size=64).map(lambda b: bytes(b"\x00\na\xff"[c & 3] for c in b)))
+    def check(t):
+        assert oracle.suffix_array_port(t).tolist() == oracle.suffix_array_bruteforce(t).tolist()
+
+    check()
+
+
+def test_oracle_search_equals_naive_scan(oracle):
+    """Reader.search of the oracle against a definition-level scan: every entry that contains
+    the pattern (as bytes, matches may start anywhere in the entry and run past its end into
+    the following text of the chunk), each once."""
+    rng = np.random.default_rng(11)
+    entries = ["".join(rng.choice(list("ab "), size=int(rng.integers(0, 12)))) for _ in range(300)]
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "n.idx")
+        w = oracle.Writer(p, 256)
+        for e in entries:
+            w.add_entry(e)
+        w.close()
+        r = oracle.Reader(p)
+        chunks = [r.chunk_text(c) for c in range(r.num_chunks)]
+        for pat in ["a", "ab", "b a", "", "aa\n", "zz", " "]:
+            want = []
+            for text in chunks:
+                starts = [0] + [i + 1 for i, ch in enumerate(text[:-1]) if ch == 10]
+                for s in starts:
+                    e = text.index(b"\n", s)
+                    # a match belongs to the entry in which it STARTS (positions s..e inclusive)
+                    if any(text.startswith(pat.encode(), k) for k in range(s, e + 1)):
+                        want.append(text[s:e].decode())
+            assert sorted(r.search(pat)) == sorted(want), pat
+        r.close()
