@@ -481,8 +481,13 @@ struct pss_reader {
     HostSink sink;
     std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
     std::vector<int64_t> per_pair;
+    // Multi-GPU front (PSS_DEVICES lists two or more devices): this object then owns no GPU
+    // state itself; subs[g] is an ordinary sharded reader on device g holding the chunks
+    // k with k % G == g, and a batch is answered by all of them concurrently.
+    std::vector<pss_reader *> subs;
 
     ~pss_reader() {
+        for (pss_reader *sub : subs) delete sub;
         if (searcher.device() >= 0) cudaSetDevice(searcher.device());
         for (auto &c : chunks) { cudaFree(c.d_text); cudaFree(c.d_sa); }
         cudaFree(d_pat); cudaFree(d_off);
@@ -502,7 +507,7 @@ static int read_exact(int fd, void *dst, size_t n, uint64_t off) {
     return 0;
 }
 
-static int reader_open(const char *path, int shard_rank, int shard_count, pss_reader **out) {
+static int reader_open(const char *path, int shard_rank, int shard_count, int device, pss_reader **out) {
     if (!path || !out) return fail(PSS_ERR_ARG, "null argument");
     *out = nullptr;
     if (shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count) return fail(PSS_ERR_ARG, "bad shard spec");
@@ -540,7 +545,7 @@ static int reader_open(const char *path, int shard_rank, int shard_count, pss_re
 
     // GPU upload of the owned chunks: text (+16 zero bytes so 4-byte text reads never leave
     // the allocation) and SA, streamed through a double pinned bounce buffer.
-    PSS_TRY(r->searcher.init(-1));
+    PSS_TRY(r->searcher.init(device));
     PSS_CUDA_TRY(cudaSetDevice(r->searcher.device()));
     cudaStream_t s = r->searcher.stream();
     PSS_CUDA_TRY(cudaEventCreate(&r->ev0));
@@ -586,12 +591,43 @@ static int reader_open(const char *path, int shard_rank, int shard_count, pss_re
 extern "C" {
 
 int32_t pss_reader_open(const char *index_file_path, pss_reader **out) {
-    return reader_open(index_file_path, 0, 1, out);
+    // PSS_DEVICES = "all" or "0,1,2,..." spreads the chunks of ONE Reader over several GPUs
+    // of the box (chunk k -> listed device k % G), inside this process.
+    std::vector<int> devices;
+    if (const char *e = std::getenv("PSS_DEVICES")) {
+        const int ndev = pss_device_count();
+        if (std::strcmp(e, "all") == 0) {
+            for (int d = 0; d < ndev; ++d) devices.push_back(d);
+        } else {
+            for (const char *q = e; *q;) {
+                char *endp = nullptr;
+                long v = std::strtol(q, &endp, 10);
+                if (endp == q) break;
+                if (v < 0 || v >= ndev) return fail(PSS_ERR_ARG, "PSS_DEVICES names a device that does not exist");
+                devices.push_back((int)v);
+                q = (*endp == ',') ? endp + 1 : endp;
+            }
+        }
+    }
+    if (devices.size() < 2) return reader_open(index_file_path, 0, 1, devices.empty() ? -1 : devices[0], out);
+    if (!out) return fail(PSS_ERR_ARG, "null argument");
+    *out = nullptr;
+    std::unique_ptr<pss_reader> front(new (std::nothrow) pss_reader());
+    if (!front) return fail(PSS_ERR_NOMEM, "out of host memory");
+    front->path = index_file_path ? index_file_path : "";
+    const int G = (int)devices.size();
+    for (int g = 0; g < G; ++g) {
+        pss_reader *sub = nullptr;
+        PSS_TRY(reader_open(index_file_path, g, G, devices[g], &sub));   // ~pss_reader frees the earlier ones
+        front->subs.push_back(sub);
+    }
+    *out = front.release();
+    return PSS_OK;
 }
 
 int32_t pss_reader_open_sharded(const char *index_file_path, int32_t shard_rank, int32_t shard_count,
                                 pss_reader **out) {
-    return reader_open(index_file_path, shard_rank, shard_count, out);
+    return reader_open(index_file_path, shard_rank, shard_count, -1, out);
 }
 
 int32_t pss_reader_close(pss_reader *r) {
@@ -599,10 +635,21 @@ int32_t pss_reader_close(pss_reader *r) {
     return PSS_OK;
 }
 
-int32_t pss_reader_num_chunks(const pss_reader *r) { return r ? (int32_t)r->chunks.size() : 0; }
-int32_t pss_reader_num_local_chunks(const pss_reader *r) { return r ? r->searcher.num_chunks() : 0; }
+int32_t pss_reader_num_chunks(const pss_reader *r) {
+    if (!r) return 0;
+    return (int32_t)(r->subs.empty() ? r->chunks.size() : r->subs[0]->chunks.size());
+}
+int32_t pss_reader_num_local_chunks(const pss_reader *r) {
+    if (!r) return 0;
+    if (r->subs.empty()) return r->searcher.num_chunks();
+    int32_t total = 0;
+    for (const pss_reader *sub : r->subs) total += sub->searcher.num_chunks();
+    return total;
+}
 
 int32_t pss_reader_chunk_text(const pss_reader *r, int32_t chunk, const uint8_t **text, int64_t *len) {
+    if (r && !r->subs.empty() && chunk >= 0)
+        return pss_reader_chunk_text(r->subs[(size_t)chunk % r->subs.size()], chunk, text, len);
     if (!r || !text || !len || chunk < 0 || chunk >= (int32_t)r->chunks.size()) return fail(PSS_ERR_ARG, "bad chunk index");
     const ChunkHost &c = r->chunks[chunk];
     *text = c.owned ? c.text.data() : nullptr;
@@ -610,10 +657,88 @@ int32_t pss_reader_chunk_text(const pss_reader *r, int32_t chunk, const uint8_t 
     return PSS_OK;
 }
 
+// Multi-GPU front: every sub-reader answers the batch for its own chunks on its own GPU (one
+// host thread each); the per-device results, each ordered by (query, chunk), are merged into
+// the single-process order: query, then ascending global chunk id.
+static int32_t search_batch_multi(pss_reader *r, const uint8_t *patterns, const int64_t *offsets, int32_t nq,
+                                  pss_result **out) {
+    const size_t G = r->subs.size();
+    std::vector<pss_result *> part(G, nullptr);
+    std::vector<int> rcs(G, PSS_OK);
+    std::vector<std::string> errs(G);
+    {
+        std::vector<std::thread> workers;
+        for (size_t g = 0; g < G; ++g)
+            workers.emplace_back([&, g] {
+                rcs[g] = pss_reader_search_batch(r->subs[g], patterns, offsets, nq, &part[g]);
+                if (rcs[g] != PSS_OK) errs[g] = pss_last_error();
+            });
+        for (auto &w : workers) w.join();
+    }
+    struct Cleanup {
+        std::vector<pss_result *> &p;
+        ~Cleanup() { for (pss_result *x : p) pss_result_free(x); }
+    } cleanup{part};
+    for (size_t g = 0; g < G; ++g)
+        if (rcs[g] != PSS_OK) return fail(rcs[g], errs[g]);
+
+    std::unique_ptr<ResultOwner> res(new (std::nothrow) ResultOwner());
+    if (!res) return fail(PSS_ERR_NOMEM, "out of host memory");
+    std::memset(&res->pub, 0, sizeof(res->pub));
+    res->query_offsets.assign((size_t)nq + 1, 0);
+    res->pool = r->pool;
+    int64_t total = 0;
+    for (size_t g = 0; g < G; ++g) total += part[g]->n_entries;
+    PSS_TRY(res->ensure(std::max<int64_t>(total, 1)));
+    std::vector<int64_t> cur(G);
+    int64_t at = 0;
+    for (int32_t q = 0; q < nq; ++q) {
+        for (size_t g = 0; g < G; ++g) cur[g] = part[g]->query_offsets[q];
+        while (true) {
+            // the sub-reader whose next entry of this query has the smallest chunk id goes next
+            int best = -1;
+            int32_t best_chunk = 0;
+            for (size_t g = 0; g < G; ++g)
+                if (cur[g] < part[g]->query_offsets[q + 1] && (best < 0 || part[g]->chunk_id[cur[g]] < best_chunk)) {
+                    best = (int)g;
+                    best_chunk = part[g]->chunk_id[cur[g]];
+                }
+            if (best < 0) break;
+            const pss_result *p = part[best];
+            int64_t end = cur[best];
+            while (end < p->query_offsets[q + 1] && p->chunk_id[end] == best_chunk) ++end;
+            const int64_t cnt = end - cur[best];
+            std::memcpy(res->chunk() + at, p->chunk_id + cur[best], (size_t)cnt * 4);
+            std::memcpy(res->start() + at, p->line_start + cur[best], (size_t)cnt * 4);
+            std::memcpy(res->end() + at, p->line_end + cur[best], (size_t)cnt * 4);
+            at += cnt;
+            cur[best] = end;
+        }
+        res->query_offsets[q + 1] = at;
+    }
+    res->used = at;
+    for (size_t g = 0; g < G; ++g) {
+        res->pub.n_hits += part[g]->n_hits;
+        res->pub.ms_bounds  = std::max(res->pub.ms_bounds, part[g]->ms_bounds);
+        res->pub.ms_extract = std::max(res->pub.ms_extract, part[g]->ms_extract);
+        res->pub.ms_dedup   = std::max(res->pub.ms_dedup, part[g]->ms_dedup);
+        res->pub.ms_total   = std::max(res->pub.ms_total, part[g]->ms_total);
+    }
+    res->pub.n_queries     = nq;
+    res->pub.n_entries     = res->used;
+    res->pub.query_offsets = res->query_offsets.data();
+    res->pub.chunk_id      = res->used ? res->chunk() : nullptr;
+    res->pub.line_start    = res->used ? res->start() : nullptr;
+    res->pub.line_end      = res->used ? res->end() : nullptr;
+    *out = &res.release()->pub;
+    return PSS_OK;
+}
+
 int32_t pss_reader_search_batch(pss_reader *r, const uint8_t *patterns, const int64_t *offsets, int32_t nq,
                                 pss_result **out) {
     if (!r || !out || nq < 0 || (nq > 0 && !offsets)) return fail(PSS_ERR_ARG, "bad search arguments");
     *out = nullptr;
+    if (!r->subs.empty()) return search_batch_multi(r, patterns, offsets, nq, out);
     std::unique_ptr<ResultOwner> res(new (std::nothrow) ResultOwner());
     if (!res) return fail(PSS_ERR_NOMEM, "out of host memory");
     std::memset(&res->pub, 0, sizeof(res->pub));
@@ -690,6 +815,8 @@ int32_t pss_reader_search_batch_device(pss_reader *r, const uint8_t *d_patterns,
         return fail(PSS_ERR_ARG, "bad search arguments");
     *n_entries = 0;
     if (n_hits) *n_hits = 0;
+    if (!r->subs.empty())
+        return fail(PSS_ERR_ARG, "device-resident search needs a single-device reader (unset PSS_DEVICES)");
     if (nq == 0 || r->searcher.num_chunks() == 0) return PSS_OK;
     DeviceSink sink(d_query_id, d_chunk_id, d_line_start, d_line_end, capacity);
     PSS_TRY(r->searcher.search(d_patterns, d_offsets, nq, static_cast<cudaStream_t>(stream), &sink, nullptr, n_hits,

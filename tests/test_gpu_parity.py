@@ -335,6 +335,34 @@ def test_sharded_readers_cover_the_index(pss, oracle):
         full.close()
 
 
+def test_multi_device_reader_front(pss, oracle, monkeypatch):
+    """PSS_DEVICES spreads the chunks of ONE Reader over several GPUs inside the process
+    (chunk k -> listed device k % G) and merges the per-device results back into the
+    single-process order.  Listing device 0 three times exercises the whole front (threads,
+    merge, text lookup) on a one-GPU box; with more GPUs visible "all" is tried as well."""
+    import pysubstringsearch
+    text = synth.zipf_words_text(1_500_000, seed=71, vocab=2048, block=1 << 16)
+    entries = bytes(text).split(b"\n")[:-1]
+    pats = synth.config2_queries(text, nq=150, seed=8) + [b"", b"e ", b"zzzz", b"\n"]
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "m.idx")
+        _write(oracle.Writer, p, entries, 1 << 18)          # 6 chunks
+        o = oracle.Reader(p)
+        specs = ["0,0,0", "0,0"] + (["all"] if pss.lib.pss_device_count() >= 2 else [])
+        for spec in specs:
+            monkeypatch.setenv("PSS_DEVICES", spec)
+            r = pss.Reader(p)
+            assert r.num_chunks == o.num_chunks
+            _compare_searches(r, o, pats)
+            _compare_searches(r, o, [pats[3]])
+            r.close()
+            pr = pysubstringsearch.Reader(index_file_path=p)
+            assert pr.search_multiple(substrings=[q.decode() for q in pats[:40]]) == o.search_multiple(pats[:40])
+            del pr
+        monkeypatch.delenv("PSS_DEVICES")
+        o.close()
+
+
 def test_device_resident_search_matches_host_api(pss):
     import torch
     text = synth.zipf_words_text(1_000_000, seed=51, vocab=2048, block=1 << 16)
