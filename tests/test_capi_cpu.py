@@ -112,3 +112,39 @@ def test_product_never_imports_oracle():
                           "import sys, pysubstringsearch_b200; print(any(m.startswith('oracle') for m in sys.modules))"],
                          cwd=ROOT, capture_output=True, text=True)
     assert out.stdout.strip() == "False", out.stderr
+
+
+def test_ctypes_structs_match_the_header(pss):
+    """ABI drift guard: sizeof/offsetof of the public structs as gcc sees include/pss.h must
+    equal the ctypes mirrors in pysubstringsearch_b200/capi.py (and INTEGRATION.md's repr(C))."""
+    import ctypes as C
+    src = r'''
+#include <stddef.h>
+#include <stdio.h>
+#include "pss.h"
+#define P(T, f) printf(#T "." #f " %zu\n", offsetof(T, f))
+int main(void) {
+    printf("pss_result %zu\n", sizeof(pss_result));
+    P(pss_result, n_queries); P(pss_result, n_entries); P(pss_result, query_offsets); P(pss_result, chunk_id);
+    P(pss_result, line_start); P(pss_result, line_end); P(pss_result, n_hits); P(pss_result, ms_bounds); P(pss_result, ms_total);
+    printf("pss_pass_stat %zu\n", sizeof(pss_pass_stat));
+    P(pss_pass_stat, shift); P(pss_pass_stat, n_records); P(pss_pass_stat, ms);
+    printf("pss_build_stats %zu\n", sizeof(pss_build_stats));
+    P(pss_build_stats, n_kernel_launches); P(pss_build_stats, active_per_round); P(pss_build_stats, total_ms);
+    P(pss_build_stats, records_sorted);
+    return 0;
+}
+'''
+    with tempfile.TemporaryDirectory() as d:
+        c, exe = os.path.join(d, "abi.c"), os.path.join(d, "abi")
+        open(c, "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        got = dict(line.rsplit(" ", 1) for line in subprocess.check_output([exe], text=True).splitlines())
+    mirrors = {"pss_result": pss.Result, "pss_pass_stat": pss.PassStat, "pss_build_stats": pss.BuildStats}
+    for key, val in got.items():
+        if "." in key:
+            struct, field = key.split(".")
+            field = {"pass": "pass_"}.get(field, field)
+            assert getattr(mirrors[struct], field).offset == int(val), key
+        else:
+            assert C.sizeof(mirrors[key]) == int(val), key
