@@ -41,6 +41,31 @@ __device__ __forceinline__ int cmp_suffix(const uint8_t *__restrict__ text, uint
     return 0;
 }
 
+// Range of SA slots whose suffixes start with P, found by the whole warp: lower bound, then
+// upper bound starting from it (the reference runs the same two searches, lib.rs:212-252).
+__device__ __forceinline__ void warp_bounds(const uint8_t *__restrict__ text, const int32_t *__restrict__ sa, uint32_t n,
+                                            const uint8_t *__restrict__ P, uint32_t m, uint32_t lane,
+                                            uint32_t *lb_out, uint32_t *cnt_out) {
+    const uint32_t pc0 = lane < m ? (uint32_t)__ldg(P + lane) : 0u;
+    // smallest slot whose suffix is >= P (as a prefix comparison)
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (cmp_suffix(text, n, (uint32_t)__ldg(sa + mid), P, m, pc0, lane) < 0) lo = mid + 1;
+        else hi = mid;
+    }
+    const uint32_t lb = lo;
+    // smallest slot past lb whose suffix is > P and does not start with it
+    hi = n;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (cmp_suffix(text, n, (uint32_t)__ldg(sa + mid), P, m, pc0, lane) <= 0) lo = mid + 1;
+        else hi = mid;
+    }
+    *lb_out  = lb;
+    *cnt_out = lo - lb;
+}
+
 __global__ void __launch_bounds__(BD_THREADS)
 bounds_kernel(const DeviceChunk *__restrict__ chunks, int nc, const uint8_t *__restrict__ patterns,
               const int64_t *__restrict__ pat_off, uint32_t npairs, uint32_t *__restrict__ lb_out,
@@ -49,33 +74,12 @@ bounds_kernel(const DeviceChunk *__restrict__ chunks, int nc, const uint8_t *__r
     const uint32_t pair = (blockIdx.x * BD_THREADS + threadIdx.x) >> 5;
     if (pair >= npairs) return;
     const uint32_t q = pair / (uint32_t)nc, c = pair % (uint32_t)nc;
-    const uint8_t *P = patterns + pat_off[q];
-    const uint32_t m = (uint32_t)(pat_off[q + 1] - pat_off[q]);
-    const uint8_t *text = chunks[c].text;
-    const int32_t *sa   = chunks[c].sa;
-    const uint32_t n    = chunks[c].n;
-    const uint32_t pc0  = lane < m ? (uint32_t)__ldg(P + lane) : 0u;
-
-    // smallest slot whose suffix is >= P (as a prefix comparison)
-    uint32_t lo = 0, hi = n;
-    while (lo < hi) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        const uint32_t s   = (uint32_t)__ldg(sa + mid);
-        if (cmp_suffix(text, n, s, P, m, pc0, lane) < 0) lo = mid + 1;
-        else hi = mid;
-    }
-    const uint32_t lb = lo;
-    // smallest slot past lb whose suffix is > P and does not start with it
-    hi = n;
-    while (lo < hi) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        const uint32_t s   = (uint32_t)__ldg(sa + mid);
-        if (cmp_suffix(text, n, s, P, m, pc0, lane) <= 0) lo = mid + 1;
-        else hi = mid;
-    }
+    uint32_t lb, cnt;
+    warp_bounds(chunks[c].text, chunks[c].sa, chunks[c].n, patterns + pat_off[q],
+                (uint32_t)(pat_off[q + 1] - pat_off[q]), lane, &lb, &cnt);
     if (lane == 0) {
         lb_out[pair]  = lb;
-        cnt_out[pair] = lo - lb;
+        cnt_out[pair] = cnt;
     }
 }
 
@@ -299,33 +303,17 @@ small_search_kernel(const DeviceChunk *__restrict__ chunks, int nc, const uint8_
     uint32_t *o_start  = reinterpret_cast<uint32_t *>(o_chunk + SMALL_CAP);
     uint32_t *o_end    = o_start + SMALL_CAP;
 
-    // ---- bounds: one warp per pair (same comparisons as bounds_kernel) ---------------------
+    // ---- bounds: one warp per pair (same search as bounds_kernel) -------------------------------
     for (uint32_t pair = warp; pair < npairs; pair += SMALL_THREADS / 32) {
         const uint32_t q = pair / (uint32_t)nc, c = pair % (uint32_t)nc;
-        const uint8_t *P = patterns + pat_off[q];
-        const uint32_t m = (uint32_t)(pat_off[q + 1] - pat_off[q]);
-        const uint8_t *text = chunks[c].text;
-        const int32_t *sa   = chunks[c].sa;
-        const uint32_t n    = chunks[c].n;
-        const uint32_t pc0  = lane < m ? (uint32_t)__ldg(P + lane) : 0u;
-        uint32_t lo = 0, hi = n;
-        while (lo < hi) {
-            const uint32_t mid = lo + ((hi - lo) >> 1);
-            if (cmp_suffix(text, n, (uint32_t)__ldg(sa + mid), P, m, pc0, lane) < 0) lo = mid + 1;
-            else hi = mid;
-        }
-        const uint32_t lb = lo;
-        hi = n;
-        while (lo < hi) {
-            const uint32_t mid = lo + ((hi - lo) >> 1);
-            if (cmp_suffix(text, n, (uint32_t)__ldg(sa + mid), P, m, pc0, lane) <= 0) lo = mid + 1;
-            else hi = mid;
-        }
+        uint32_t lb, cnt;
+        warp_bounds(chunks[c].text, chunks[c].sa, chunks[c].n, patterns + pat_off[q],
+                    (uint32_t)(pat_off[q + 1] - pat_off[q]), lane, &lb, &cnt);
         if (lane == 0) {
             s.lb[pair] = lb;
-            s.cnt[pair] = lo - lb;
+            s.cnt[pair] = cnt;
             lb_out[pair] = lb;
-            cnt_out[pair] = lo - lb;
+            cnt_out[pair] = cnt;
         }
     }
     if (tid < SMALL_MAX_PAIRS) s.pair_entries[tid] = 0;
