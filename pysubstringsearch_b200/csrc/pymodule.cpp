@@ -29,9 +29,24 @@ PyObject *raise_status(int rc) {
 }
 
 // ---- Writer ---------------------------------------------------------------------------
+// pyo3 hands out `&mut self` for every method of the reference's classes (lib.rs:67,88,105,
+// 126,201): a second thread entering while a call is in flight gets RuntimeError("Already
+// borrowed").  The GIL is released around the native calls here, so the same exclusivity
+// is enforced explicitly (the C handles are not thread-safe).
+struct BorrowGuard {
+    bool *flag;
+    bool  ok;
+    explicit BorrowGuard(bool *f) : flag(f), ok(!*f) {
+        if (ok) *flag = true;
+        else PyErr_SetString(PyExc_RuntimeError, "Already borrowed");
+    }
+    ~BorrowGuard() { if (ok) *flag = false; }
+};
+
 struct WriterObject {
     PyObject_HEAD
     pss_writer *w;
+    bool busy;
 };
 
 int Writer_init(WriterObject *self, PyObject *args, PyObject *kwds) {
@@ -82,6 +97,8 @@ PyObject *Writer_add_entry(WriterObject *self, PyObject *args, PyObject *kwds) {
     Py_ssize_t len = 0;
     const char *p = PyUnicode_AsUTF8AndSize(text, &len);
     if (!p) return nullptr;
+    BorrowGuard guard(&self->busy);
+    if (!guard.ok) return nullptr;
     int rc = pss_writer_add_entry(self->w, reinterpret_cast<const uint8_t *>(p), (size_t)len);
     if (rc != PSS_OK) return raise_status(rc);
     Py_RETURN_NONE;
@@ -94,6 +111,8 @@ PyObject *Writer_add_entries_from_file_lines(WriterObject *self, PyObject *args,
     const char *path = PyUnicode_AsUTF8(path_obj);
     if (!path) return nullptr;
     std::string path_copy(path);
+    BorrowGuard guard(&self->busy);
+    if (!guard.ok) return nullptr;
     int rc;
     Py_BEGIN_ALLOW_THREADS
     rc = pss_writer_add_entries_from_file_lines(self->w, path_copy.c_str());
@@ -103,6 +122,8 @@ PyObject *Writer_add_entries_from_file_lines(WriterObject *self, PyObject *args,
 }
 
 PyObject *Writer_dump_data(WriterObject *self, PyObject *) {
+    BorrowGuard guard(&self->busy);
+    if (!guard.ok) return nullptr;
     int rc;
     Py_BEGIN_ALLOW_THREADS
     rc = pss_writer_dump_data(self->w);
@@ -112,6 +133,8 @@ PyObject *Writer_dump_data(WriterObject *self, PyObject *) {
 }
 
 PyObject *Writer_finalize(WriterObject *self, PyObject *) {
+    BorrowGuard guard(&self->busy);
+    if (!guard.ok) return nullptr;
     int rc;
     Py_BEGIN_ALLOW_THREADS
     rc = pss_writer_finalize(self->w);
@@ -134,6 +157,7 @@ PyTypeObject WriterType = {PyVarObject_HEAD_INIT(nullptr, 0)};
 struct ReaderObject {
     PyObject_HEAD
     pss_reader *r;
+    bool busy;
 };
 
 int Reader_init(ReaderObject *self, PyObject *args, PyObject *kwds) {
@@ -183,6 +207,8 @@ inline PyObject *make_str(const uint8_t *p, size_t n) {
 
 // One batched native search; returns the concatenated list of entries (query order).
 PyObject *run_batch(ReaderObject *self, const std::vector<uint8_t> &blob, const std::vector<int64_t> &offsets) {
+    BorrowGuard guard(&self->busy);
+    if (!guard.ok) return nullptr;
     pss_result *res = nullptr;
     int rc;
     const int32_t nq = (int32_t)offsets.size() - 1;
