@@ -1,0 +1,1 @@
+"""Developer tools: synthetic corpora, ncu drivers, launch-list summaries."""
