@@ -38,7 +38,7 @@ extern "C" {
 /* Message describing the last failure on the calling thread ("" if none). */
 const char *pss_last_error(void);
 
-/* Library version string, e.g. "pss_b200 0.1 (sm_100a)". */
+/* Library version string, e.g. "pss_b200 0.2 (sm_100a)". */
 const char *pss_version(void);
 
 /* Number of CUDA devices visible to the library (0 if none / driver missing). */
@@ -72,6 +72,32 @@ int32_t pss_get_device(void);
  * a proper prefix sorting first.
  */
 int32_t pss_libsais(const uint8_t *T, int32_t *SA, int32_t n, int32_t fs, int32_t *freq);
+
+/*
+ * Asynchronous form of the same seam: lets the caller overlap the build of
+ * chunk k with the ingestion of chunk k+1 (the reference blocks inside dump_data,
+ * src/lib.rs:105-124 → :115) and spread chunks over the GPUs of the box.
+ *
+ *   pss_sa_build_begin(device, T, n, &h)   queues the build on `device` (-1 = default) and
+ *                                          returns at once; T must stay valid and unchanged
+ *                                          until pss_sa_build_wait(h, ..) returns
+ *   pss_sa_build_wait(h, SA)               blocks until the build is done, copies SA[0..n)
+ *                                          to host memory (pinned or pageable), frees h
+ *
+ * Each device runs its builds in begin order on one worker thread and keeps two
+ * (text, SA) slots in HBM: the device→host copy done by wait(k) overlaps H2D + build of
+ * k+1.  Wait for the handles of one device in begin order, with at most two of them
+ * begun-but-not-waited ahead of the one being waited for.  Same return codes as pss_libsais.
+ */
+typedef struct pss_sa_build pss_sa_build;
+int32_t pss_sa_build_begin(int32_t device, const uint8_t *T, int32_t n, pss_sa_build **out);
+int32_t pss_sa_build_wait(pss_sa_build *h, int32_t *SA);
+
+/* pss_libsais, the async builds and the Writers share one cached build engine per GPU
+ * (≈ 32 bytes of HBM per text byte of the largest chunk seen, plus two text/SA slots).
+ * This frees the device memory of every engine with nothing in flight; it regrows on
+ * demand. */
+int32_t pss_release_cached(void);
 
 /* Reusable builder: owns the device workspace (≈ 32 bytes per text byte of capacity). */
 typedef struct pss_sa_builder pss_sa_builder;
@@ -155,15 +181,29 @@ typedef struct pss_writer pss_writer;
  * (src/lib.rs:50-65).  max_chunk_len < 0 means "None" → 512 MiB default (:57). */
 int32_t pss_writer_open(const char *index_file_path, int64_t max_chunk_len, pss_writer **out);
 
+/* Same, with an explicit chunk → GPU map: chunk k of this writer is built on
+ * devices[k % ndev] (ndev >= 1).  pss_writer_open uses env PSS_DEVICES ("all" or
+ * "0,1,..") if set, else the default device.  Chunks are built concurrently (one engine
+ * per listed GPU) while ingestion continues; records still reach the file strictly in
+ * chunk order, so the container is byte-identical to the single-GPU / reference one. */
+int32_t pss_writer_open_devices(const char *index_file_path, int64_t max_chunk_len,
+                                const int32_t *devices, int32_t ndev, pss_writer **out);
+
 /* src/lib.rs:88-103.  `text` is the entry's UTF-8 bytes (no terminator needed).
  * PSS_ERR_TOOBIG if len > capacity. */
 int32_t pss_writer_add_entry(pss_writer *w, const uint8_t *text, size_t len);
+
+/* 1 when adding an entry of `len` bytes would hand the buffered chunk to the builder first
+ * (bindings use it to release their interpreter lock only around such calls). */
+int32_t pss_writer_would_flush(const pss_writer *w, size_t len);
 
 /* src/lib.rs:67-86 (bstr for_byte_line: split at '\n', strip "\n" or "\r\n"). */
 int32_t pss_writer_add_entries_from_file_lines(pss_writer *w, const char *input_file_path);
 
 /* src/lib.rs:105-124: serialise the buffered chunk (u32le n, text, u32le 4n, i32le SA[n])
- * with the SA built on the GPU; no-op on an empty buffer. */
+ * with the SA built on the GPU; no-op on an empty buffer.  The build and the file write
+ * proceed in the background (records reach the file in chunk order); a failure of either
+ * is reported by the next dump / finalize / close. */
 int32_t pss_writer_dump_data(pss_writer *w);
 
 /* src/lib.rs:126-135: dump the last partial chunk and flush. */
@@ -198,6 +238,8 @@ typedef struct pss_result {
     float           ms_extract;     /* device time: hit expansion + newline extraction */
     float           ms_dedup;       /* device time: sort-based dedup + compaction */
     float           ms_total;       /* device time of the whole batch, incl. H2D/D2H */
+    float           ms_exchange;    /* multi-GPU: NCCL broadcast + gather + placement on rank 0 (0 otherwise) */
+    int32_t         n_ranks;        /* ranks that contributed (1 for a single-process reader) */
 } pss_result;
 
 /* Reader::new (src/lib.rs:162-199): parse the container, keep every chunk's text in host
@@ -209,6 +251,29 @@ int32_t pss_reader_open(const char *index_file_path, pss_reader **out);
  * (chunk → GPU map for one-process-per-GPU runs).  Text of foreign chunks is not kept. */
 int32_t pss_reader_open_sharded(const char *index_file_path, int32_t shard_rank,
                                 int32_t shard_count, pss_reader **out);
+
+/* Same as pss_reader_open with an explicit chunk → GPU map inside this process: chunk k
+ * lives on devices[k % ndev]; a batch is answered by all listed GPUs concurrently and
+ * merged into the single-process order.  (pss_reader_open reads the same list from env
+ * PSS_DEVICES = "all" | "0,1,..".) */
+int32_t pss_reader_open_devices(const char *index_file_path, const int32_t *devices, int32_t ndev,
+                                pss_reader **out);
+
+/* A reader over chunks that already sit in this process's GPU memory (e.g. suffix arrays
+ * just built with pss_sa_builder_build_device): no file, no copy — the pointers are
+ * borrowed and must outlive the reader.  d_text must be 16-byte aligned with 16 readable
+ * bytes past n; h_text (host copy of the text, may be NULL) is what
+ * pss_reader_chunk_text returns.  global_id is the chunk's index in the whole index
+ * (ascending within one reader). */
+typedef struct pss_device_chunk {
+    const uint8_t *d_text;
+    const int32_t *d_sa;
+    const uint8_t *h_text;
+    uint32_t       n;
+    int32_t        global_id;
+} pss_device_chunk;
+int32_t pss_reader_open_device_chunks(const pss_device_chunk *chunks, int32_t n_local,
+                                      int32_t n_chunks_total, int32_t device, pss_reader **out);
 
 int32_t pss_reader_close(pss_reader *r);
 
@@ -222,8 +287,9 @@ int32_t pss_reader_chunk_text(const pss_reader *r, int32_t chunk, const uint8_t 
 
 /*
  * Batched search (Reader.search = batch of one; search_multiple = one call).
- * patterns: concatenated pattern bytes (HOST); offsets[nq+1] (HOST, offsets[0] = 0):
- * pattern q is patterns[offsets[q] .. offsets[q+1]).  Empty patterns are legal (match
+ * patterns: concatenated pattern bytes (HOST); offsets[nq+1] (HOST, offsets[0] = 0,
+ * non-decreasing — checked, PSS_ERR_ARG otherwise): pattern q is
+ * patterns[offsets[q] .. offsets[q+1]).  Empty patterns are legal (match
  * every entry).  On success *out is a new result (free with pss_result_free).
  * The handle is not thread-safe (mirrors `&mut self`, lib.rs:202).
  */
@@ -231,20 +297,71 @@ int32_t pss_reader_search_batch(pss_reader *r, const uint8_t *patterns, const in
                                 int32_t nq, pss_result **out);
 
 /*
- * Same search with DEVICE-resident inputs and outputs, for one-process-per-GPU runs that
- * gather hits with NCCL: d_patterns / d_offsets are device pointers; the result tuples
- * are left on the device in caller-provided buffers of `capacity` entries each
- * (d_query_id, d_chunk_id, d_line_start, d_line_end).  *n_entries receives the number
- * of entries produced; if it exceeds `capacity` nothing past capacity is written and
- * PSS_ERR_NOMEM is returned (call again with larger buffers).
+ * Result of a device-resident search: DEVICE pointers owned by the reader, valid until
+ * its next search.  Entries are ordered as in pss_result; pair p = query * n_chunks +
+ * chunk position (position among the chunks this result covers, ascending chunk id).
+ */
+typedef struct pss_device_result {
+    int32_t         n_queries;
+    int32_t         n_chunks;        /* chunks covered: local chunks, or all of them after a gather */
+    int64_t         n_entries;
+    int64_t         n_hits;
+    const int64_t  *d_query_offsets; /* [n_queries + 1] */
+    const uint32_t *d_entry_offsets; /* [n_queries * n_chunks + 1] entries before pair p */
+    const int32_t  *d_chunk_id;      /* [n_entries] */
+    const uint32_t *d_line_start;    /* [n_entries] */
+    const uint32_t *d_line_end;      /* [n_entries] */
+    float           ms_bounds, ms_extract, ms_dedup, ms_exchange;
+} pss_device_result;
+
+/*
+ * Same search with DEVICE-resident inputs and outputs: d_patterns / d_offsets are device
+ * pointers on the reader's GPU (total_pattern_bytes = offsets[nq], known to the caller);
+ * the tuples stay in HBM.  `stream` is a cudaStream_t (NULL = the reader's own stream);
+ * the call returns after the batch has completed on the device.  Single-device readers only.
  */
 int32_t pss_reader_search_batch_device(pss_reader *r, const uint8_t *d_patterns,
                                        const int64_t *d_offsets, int32_t nq,
-                                       int64_t total_pattern_bytes,
-                                       int32_t *d_query_id, int32_t *d_chunk_id,
-                                       uint32_t *d_line_start, uint32_t *d_line_end,
-                                       int64_t capacity, int64_t *n_entries,
-                                       int64_t *n_hits, void *stream);
+                                       int64_t total_pattern_bytes, pss_device_result *out,
+                                       void *stream);
+
+/* ===================================================================================== */
+/* One process per GPU: sharded index, hits gathered to rank 0 over NCCL                  */
+/* (reference: rayon fan-out over chunks + Mutex<Vec>::extend, src/lib.rs:205-207,280-284) */
+/* ===================================================================================== */
+
+/*
+ * Communicator of the search exchange step.  Rank 0 creates a 128-byte id
+ * (pss_comm_unique_id) and hands it to the other ranks by any means (the launcher's store,
+ * a file, torch.distributed.broadcast); every rank then calls pss_comm_create — a
+ * collective — with its rank and the world size, on the GPU selected by
+ * pss_set_device / PSS_DEVICE / LOCAL_RANK.  Built on NCCL (NVLink / NVSwitch).
+ */
+typedef struct pss_comm pss_comm;
+#define PSS_COMM_ID_BYTES 128
+int32_t pss_comm_unique_id(uint8_t id[PSS_COMM_ID_BYTES]);
+int32_t pss_comm_create(const uint8_t id[PSS_COMM_ID_BYTES], int32_t rank, int32_t world, pss_comm **out);
+int32_t pss_comm_destroy(pss_comm *c);
+
+/*
+ * Collective batched search over an index sharded chunk k → rank k % world (readers opened
+ * with pss_reader_open_sharded(path, rank, world) or pss_reader_open_device_chunks).
+ * Every rank calls it with the same nq and the same offsets[] (host); pattern bytes are
+ * taken from rank 0 and broadcast (other ranks may pass patterns = NULL).  Each rank
+ * searches its own chunks; rank 0 receives exactly the tuples found (no padding), places
+ * them in the single-process order (query, ascending chunk id, SA order) and returns them
+ * in *out; on other ranks *out is an empty result.  One exchange step per batch:
+ * broadcast(patterns) → local search → gather-v(entry offsets, tuples) → placement.
+ */
+int32_t pss_reader_search_batch_dist(pss_reader *r, pss_comm *c, const uint8_t *patterns,
+                                     const int64_t *offsets, int32_t nq, pss_result **out);
+
+/* Same exchange with the batch already in rank 0's HBM (d_patterns, d_offsets valid on
+ * rank 0 only; nq and total_pattern_bytes identical on every rank) and the merged tuples
+ * left in rank 0's HBM (*out; n_entries = 0 elsewhere). */
+int32_t pss_reader_search_batch_dist_device(pss_reader *r, pss_comm *c, const uint8_t *d_patterns,
+                                            const int64_t *d_offsets, int32_t nq,
+                                            int64_t total_pattern_bytes, pss_device_result *out);
 
 void pss_result_free(pss_result *res);
 

@@ -36,8 +36,20 @@ lib.pss_reader_num_chunks.argtypes = [vp]
 lib.pss_reader_num_local_chunks.argtypes = [vp]
 lib.pss_reader_chunk_text.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64)]
 lib.pss_reader_search_batch.argtypes = [vp, vp, vp, i32, C.POINTER(vp)]
-lib.pss_reader_search_batch_device.argtypes = [vp, vp, vp, i32, i64, vp, vp, vp, vp, i64, C.POINTER(i64),
-                                               C.POINTER(i64), vp]
+lib.pss_reader_search_batch_device.argtypes = [vp, vp, vp, i32, i64, vp, vp]
+lib.pss_sa_build_begin.argtypes = [i32, vp, i32, C.POINTER(vp)]
+lib.pss_sa_build_wait.argtypes = [vp, vp]
+lib.pss_release_cached.argtypes = []
+lib.pss_writer_open_devices.argtypes = [C.c_char_p, i64, vp, i32, C.POINTER(vp)]
+lib.pss_writer_would_flush.argtypes = [vp, sz]
+lib.pss_reader_open_devices.argtypes = [C.c_char_p, vp, i32, C.POINTER(vp)]
+lib.pss_reader_open_device_chunks.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
+lib.pss_comm_unique_id.argtypes = [vp]
+lib.pss_comm_create.argtypes = [vp, i32, i32, C.POINTER(vp)]
+lib.pss_comm_destroy.argtypes = [vp]
+lib.pss_reader_search_batch_dist.argtypes = [vp, vp, vp, vp, i32, C.POINTER(vp)]
+lib.pss_reader_search_batch_dist_device.argtypes = [vp, vp, vp, vp, i32, i64, vp]
+COMM_ID_BYTES = 128
 lib.pss_result_free.argtypes = [vp]
 lib.pss_result_free.restype = None
 
@@ -58,7 +70,19 @@ class Result(C.Structure):
     _fields_ = [("n_queries", i32), ("reserved", i32), ("n_entries", i64), ("query_offsets", C.POINTER(i64)),
                 ("chunk_id", C.POINTER(i32)), ("line_start", C.POINTER(C.c_uint32)),
                 ("line_end", C.POINTER(C.c_uint32)), ("n_hits", i64), ("ms_bounds", C.c_float),
-                ("ms_extract", C.c_float), ("ms_dedup", C.c_float), ("ms_total", C.c_float)]
+                ("ms_extract", C.c_float), ("ms_dedup", C.c_float), ("ms_total", C.c_float),
+                ("ms_exchange", C.c_float), ("n_ranks", i32)]
+
+
+class DeviceChunk(C.Structure):
+    _fields_ = [("d_text", vp), ("d_sa", vp), ("h_text", vp), ("n", C.c_uint32), ("global_id", i32)]
+
+
+class DeviceResult(C.Structure):
+    _fields_ = [("n_queries", i32), ("n_chunks", i32), ("n_entries", i64), ("n_hits", i64),
+                ("d_query_offsets", vp), ("d_entry_offsets", vp), ("d_chunk_id", vp), ("d_line_start", vp),
+                ("d_line_end", vp), ("ms_bounds", C.c_float), ("ms_extract", C.c_float), ("ms_dedup", C.c_float),
+                ("ms_exchange", C.c_float)]
 
 
 def err():
@@ -77,10 +101,63 @@ def libsais(text):
     return sa
 
 
-class Writer:
-    def __init__(self, path, max_chunk_len=None):
+def result_arrays(res):
+    """pss_result* (c_void_p) → (query_offsets, chunk, start, end, stats) numpy copies; frees the result."""
+    r = C.cast(res, C.POINTER(Result)).contents
+    n, nq = r.n_entries, r.n_queries
+    qo = np.ctypeslib.as_array(r.query_offsets, (nq + 1,)).copy()
+    if n:
+        ch = np.ctypeslib.as_array(r.chunk_id, (n,)).copy()
+        st = np.ctypeslib.as_array(r.line_start, (n,)).copy()
+        en = np.ctypeslib.as_array(r.line_end, (n,)).copy()
+    else:
+        ch = np.zeros(0, np.int32)
+        st = en = np.zeros(0, np.uint32)
+    stats = dict(n_hits=r.n_hits, ms_bounds=r.ms_bounds, ms_extract=r.ms_extract, ms_dedup=r.ms_dedup,
+                 ms_total=r.ms_total, ms_exchange=r.ms_exchange, n_ranks=r.n_ranks)
+    lib.pss_result_free(res)
+    return qo, ch, st, en, stats
+
+
+def pack(patterns):
+    pats = [p.encode() if isinstance(p, str) else bytes(p) for p in patterns]
+    offs = np.zeros(len(pats) + 1, dtype=np.int64)
+    if pats:
+        np.cumsum([len(p) for p in pats], out=offs[1:])
+    blob = np.frombuffer(b"".join(pats) + b"\0", dtype=np.uint8).copy()
+    return blob, offs
+
+
+class Comm:
+    """Communicator of the distributed search (NCCL inside libpss_b200.so).  `exchange(id_bytes)`
+    must hand rank 0's id to every rank (e.g. a torch.distributed broadcast)."""
+
+    def __init__(self, rank, world, exchange=None):
         self.h = vp()
-        check(lib.pss_writer_open(os.fsencode(path), -1 if max_chunk_len is None else max_chunk_len, C.byref(self.h)))
+        ident = (C.c_uint8 * COMM_ID_BYTES)()
+        if world > 1:
+            if rank == 0:
+                check(lib.pss_comm_unique_id(ident))
+            raw = exchange(bytes(ident))
+            ident = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(raw)
+        check(lib.pss_comm_create(ident, rank, world, C.byref(self.h)))
+        self.rank, self.world = rank, world
+
+    def close(self):
+        if self.h:
+            lib.pss_comm_destroy(self.h)
+            self.h = None
+
+
+class Writer:
+    def __init__(self, path, max_chunk_len=None, devices=None):
+        self.h = vp()
+        mcl = -1 if max_chunk_len is None else max_chunk_len
+        if devices is None:
+            check(lib.pss_writer_open(os.fsencode(path), mcl, C.byref(self.h)))
+        else:
+            arr = (i32 * len(devices))(*devices)
+            check(lib.pss_writer_open_devices(os.fsencode(path), mcl, arr, len(devices), C.byref(self.h)))
 
     def add_entry(self, text):
         b = text.encode() if isinstance(text, str) else bytes(text)
@@ -104,9 +181,16 @@ class Writer:
 
 
 class Reader:
-    def __init__(self, path, shard=None):
+    def __init__(self, path=None, shard=None, devices=None, device_chunks=None, n_chunks_total=None, device=-1):
         self.h = vp()
-        if shard is None:
+        if device_chunks is not None:
+            arr = (DeviceChunk * len(device_chunks))(*device_chunks)
+            self._keep = arr
+            check(lib.pss_reader_open_device_chunks(arr, len(device_chunks), n_chunks_total, device, C.byref(self.h)))
+        elif devices is not None:
+            arr = (i32 * len(devices))(*devices)
+            check(lib.pss_reader_open_devices(os.fsencode(path), arr, len(devices), C.byref(self.h)))
+        elif shard is None:
             check(lib.pss_reader_open(os.fsencode(path), C.byref(self.h)))
         else:
             check(lib.pss_reader_open_sharded(os.fsencode(path), shard[0], shard[1], C.byref(self.h)))
@@ -122,24 +206,15 @@ class Reader:
 
     def search_batch(self, patterns):
         """→ (query_offsets, chunk, start, end, stats dict); ordered as the reference orders."""
-        pats = [p.encode() if isinstance(p, str) else bytes(p) for p in patterns]
-        offs = np.zeros(len(pats) + 1, dtype=np.int64)
-        if pats:
-            np.cumsum([len(p) for p in pats], out=offs[1:])
-        blob = np.frombuffer(b"".join(pats) + b"\0", dtype=np.uint8).copy()
+        blob, offs = pack(patterns)
         res = vp()
-        check(lib.pss_reader_search_batch(self.h, blob.ctypes.data, offs.ctypes.data, len(pats), C.byref(res)))
-        r = C.cast(res, C.POINTER(Result)).contents
-        n, nq = r.n_entries, r.n_queries
-        qo = np.ctypeslib.as_array(r.query_offsets, (nq + 1,)).copy()
-        if n:
-            ch = np.ctypeslib.as_array(r.chunk_id, (n,)).copy()
-            st = np.ctypeslib.as_array(r.line_start, (n,)).copy()
-            en = np.ctypeslib.as_array(r.line_end, (n,)).copy()
-        else:
-            ch = np.zeros(0, np.int32)
-            st = en = np.zeros(0, np.uint32)
-        stats = dict(n_hits=r.n_hits, ms_bounds=r.ms_bounds, ms_extract=r.ms_extract, ms_dedup=r.ms_dedup,
-                     ms_total=r.ms_total)
-        lib.pss_result_free(res)
-        return qo, ch, st, en, stats
+        check(lib.pss_reader_search_batch(self.h, blob.ctypes.data, offs.ctypes.data, len(offs) - 1, C.byref(res)))
+        return result_arrays(res)
+
+    def search_batch_dist(self, comm, patterns):
+        """Collective (every rank calls it with the same patterns); rank 0 gets the merged result."""
+        blob, offs = pack(patterns)
+        res = vp()
+        check(lib.pss_reader_search_batch_dist(self.h, comm.h, blob.ctypes.data, offs.ctypes.data, len(offs) - 1,
+                                               C.byref(res)))
+        return result_arrays(res)

@@ -5,6 +5,7 @@
 #include <mutex>
 #include <new>
 
+#include "build_engine.cuh"
 #include "common.cuh"
 #include "radix_sort.cuh"
 #include "sa_build.cuh"
@@ -45,25 +46,6 @@ int sm_count(int device) {
     return v;
 }
 
-// Cached builder behind pss_libsais (grow-only workspace, one per process).
-static std::mutex g_builder_mu;
-static SaBuilder *g_builder = nullptr;
-
-static int global_builder(SaBuilder **out) {
-    if (!g_builder) {
-        SaBuilder *b = new (std::nothrow) SaBuilder();
-        if (!b) return fail(PSS_ERR_NOMEM, "out of host memory");
-        int rc = b->init(-1, 0);
-        if (rc != PSS_OK) {
-            delete b;
-            return rc;
-        }
-        g_builder = b;
-    }
-    *out = g_builder;
-    return PSS_OK;
-}
-
 }  // namespace pss
 
 using namespace pss;
@@ -76,7 +58,7 @@ extern "C" {
 
 const char *pss_last_error(void) { return t_last_error.c_str(); }
 
-const char *pss_version(void) { return "pss_b200 0.1 (sm_100a)"; }
+const char *pss_version(void) { return "pss_b200 0.2 (sm_100a)"; }
 
 int32_t pss_device_count(void) {
     int n = 0;
@@ -106,10 +88,35 @@ int32_t pss_libsais(const uint8_t *T, int32_t *SA, int32_t n, int32_t fs, int32_
         for (int32_t i = 0; i < n; ++i) freq[T[i]]++;
     }
     if (n == 0) return PSS_OK;
-    std::lock_guard<std::mutex> lock(g_builder_mu);
-    SaBuilder *b = nullptr;
-    PSS_TRY(global_builder(&b));
-    return b->build_host(T, n, SA);
+    // the synchronous seam is the asynchronous one waited for at once (same cached engine)
+    BuildEngine *engine = nullptr;
+    PSS_TRY(BuildEngine::get(-1, &engine));
+    BuildEngine::Job *job = nullptr;
+    PSS_TRY(engine->begin(T, n, &job));
+    return engine->wait(job, SA);
+}
+
+int32_t pss_sa_build_begin(int32_t device, const uint8_t *T, int32_t n, pss_sa_build **out) {
+    if (!out) return fail(PSS_ERR_ARG, "null out pointer");
+    *out = nullptr;
+    if (n < 0 || (n > 0 && !T)) return fail(PSS_ERR_ARG, "bad build arguments");
+    BuildEngine *engine = nullptr;
+    PSS_TRY(BuildEngine::get(device, &engine));
+    BuildEngine::Job *job = nullptr;
+    PSS_TRY(engine->begin(T, n, &job));
+    *out = reinterpret_cast<pss_sa_build *>(job);
+    return PSS_OK;
+}
+
+int32_t pss_sa_build_wait(pss_sa_build *h, int32_t *SA) {
+    if (!h) return fail(PSS_ERR_ARG, "null build handle");
+    BuildEngine::Job *job = reinterpret_cast<BuildEngine::Job *>(h);
+    return job->engine->wait(job, SA);
+}
+
+int32_t pss_release_cached(void) {
+    BuildEngine::release_idle();
+    return PSS_OK;
 }
 
 int32_t pss_sa_builder_create(int32_t device, int64_t max_n, pss_sa_builder **out) {

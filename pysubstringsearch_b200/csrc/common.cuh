@@ -60,6 +60,12 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // Streaming (read-once) loads: keep them out of L1 so the staging tiles own it.
 __device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t *p) {
     uint64_t v;

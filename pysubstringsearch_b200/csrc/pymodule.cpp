@@ -99,7 +99,17 @@ PyObject *Writer_add_entry(WriterObject *self, PyObject *args, PyObject *kwds) {
     if (!p) return nullptr;
     BorrowGuard guard(&self->busy);
     if (!guard.ok) return nullptr;
-    int rc = pss_writer_add_entry(self->w, reinterpret_cast<const uint8_t *>(p), (size_t)len);
+    int rc;
+    if (pss_writer_would_flush(self->w, (size_t)len)) {
+        // this entry hands the buffered chunk to the GPU builder and may wait for a free
+        // pipeline slot: other Python threads run meanwhile.  `p` stays valid: `text` is
+        // referenced by the caller's argument tuple, and BorrowGuard keeps the handle ours.
+        Py_BEGIN_ALLOW_THREADS
+        rc = pss_writer_add_entry(self->w, reinterpret_cast<const uint8_t *>(p), (size_t)len);
+        Py_END_ALLOW_THREADS
+    } else {
+        rc = pss_writer_add_entry(self->w, reinterpret_cast<const uint8_t *>(p), (size_t)len);
+    }
     if (rc != PSS_OK) return raise_status(rc);
     Py_RETURN_NONE;
 }
@@ -178,8 +188,11 @@ int Reader_init(ReaderObject *self, PyObject *args, PyObject *kwds) {
 
 void Reader_dealloc(ReaderObject *self) {
     if (self->r) {
-        pss_reader_close(self->r);
+        pss_reader *r = self->r;
         self->r = nullptr;
+        Py_BEGIN_ALLOW_THREADS      // frees gigabytes of GPU and host memory
+        pss_reader_close(r);
+        Py_END_ALLOW_THREADS
     }
     Py_TYPE(self)->tp_free(reinterpret_cast<PyObject *>(self));
 }

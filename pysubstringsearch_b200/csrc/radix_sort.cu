@@ -13,7 +13,9 @@ constexpr uint32_t FLAG_EMPTY = 0u;
 constexpr uint32_t FLAG_LOCAL = 1u;  // value = this tile's count
 constexpr uint32_t FLAG_INCL  = 2u;  // value = inclusive prefix over tiles 0..t
 constexpr uint32_t FLAG_ABORT = 3u;  // a predecessor gave up (watchdog)
-constexpr uint32_t SPIN_LIMIT = 1u << 22;
+// Look-back watchdog: a wall-clock limit (not a poll count), so that a predecessor tile
+// slowed down by time-slicing, MPS or a debugger does not turn into a spurious failure.
+constexpr uint64_t WATCHDOG_NS = 30ull * 1000ull * 1000ull * 1000ull;
 
 constexpr int CTRL_TICKET  = 0;   // [0..8)
 constexpr int CTRL_ERROR   = 8;
@@ -293,10 +295,15 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict_
     if (tid < RADIX) {
         if (tile > 0) {
             uint32_t spins = 0;
+            uint64_t t0 = 0;
             while (true) {
                 lb_consume();
                 if (lb_done) break;
-                if (!lb_progress && ++spins >= SPIN_LIMIT) { lb_abort = true; break; }
+                if (!lb_progress && (++spins & 0x3FFFu) == 0) {
+                    const uint64_t now = global_timer_ns();
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > WATCHDOG_NS) { lb_abort = true; break; }
+                }
                 lb_issue();
             }
             const bool aborted = lb_abort;
@@ -399,6 +406,14 @@ int RadixSorter::ensure(int64_t n) {
     return PSS_OK;
 }
 
+void RadixSorter::release_workspace() {
+    if (device_ < 0) return;
+    cudaSetDevice(device_);
+    cudaFree(d_tile_state_);
+    d_tile_state_  = nullptr;
+    tile_capacity_ = 0;
+}
+
 void RadixSorter::release() {
     if (device_ < 0) return;
     cudaSetDevice(device_);
@@ -449,11 +464,70 @@ int RadixSorter::partition(uint64_t *keys, uint64_t *keys_alt, uint32_t n, int s
     return PSS_OK;
 }
 
-// Reads back the look-back watchdog flag (synchronises the stream).
+// Reads back the look-back watchdog flag (synchronises the stream) and clears it.
 int RadixSorter::poll_error(cudaStream_t stream) {
     PSS_CUDA_TRY(cudaMemcpyAsync(h_ctrl_, d_ctrl_, CTRL_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     PSS_CUDA_TRY(cudaStreamSynchronize(stream));
-    if (h_ctrl_[CTRL_ERROR]) return fail(PSS_ERR_CUDA, "radix sort: look-back watchdog fired");
+    if (h_ctrl_[CTRL_ERROR]) {
+        PSS_CUDA_TRY(cudaMemsetAsync(d_ctrl_ + CTRL_ERROR, 0, sizeof(uint32_t), stream));
+        return fail(PSS_ERR_CUDA, "radix sort: look-back watchdog fired");
+    }
+    return PSS_OK;
+}
+
+const uint32_t *RadixSorter::d_error_flag() const { return d_ctrl_ + CTRL_ERROR; }
+
+int RadixSorter::sort_async(uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, uint32_t *vals_alt, uint32_t n,
+                            int begin_bit, int end_bit, bool iota_vals, cudaStream_t stream, bool *in_alt) {
+    *in_alt = false;
+    if (begin_bit < 0 || end_bit > 64 || end_bit < begin_bit) return fail(PSS_ERR_ARG, "radix sort: bad bit range");
+    if (n > VALUE_MASK) return fail(PSS_ERR_ARG, "radix sort: n must be < 2^30");
+    const int npass = (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS;
+    if (npass > MAX_PASSES) return fail(PSS_ERR_ARG, "radix sort: more than 8 digits");
+    if (n == 0) return PSS_OK;
+    if (npass == 0) {
+        if (iota_vals) {
+            iota_kernel<<<(unsigned)div_up(n, 256), 256, 0, stream>>>(vals, n);
+            PSS_LAUNCH_CHECK();
+        }
+        return PSS_OK;
+    }
+    PSS_TRY(ensure(n));
+    const int last_bits      = (end_bit - begin_bit) - (npass - 1) * RADIX_BITS;
+    const uint32_t last_mask = (1u << last_bits) - 1u;
+    const uint32_t tiles     = (uint32_t)div_up(n, tile_items_);
+    const PassConfig &pc     = kPassConfigs[cfg_];
+    PSS_CUDA_TRY(cudaMemsetAsync(d_hist_, 0, MAX_PASSES * RADIX * sizeof(uint32_t), stream));
+    PSS_CUDA_TRY(cudaMemsetAsync(d_ctrl_, 0, CTRL_ERROR * sizeof(uint32_t), stream));   // tickets only: the error flag is sticky
+    {
+        int64_t want = div_up(n, (int64_t)HIST_THREADS * HIST_UNROLL);
+        int grid     = (int)std::min<int64_t>(want, (int64_t)num_sms_ * 4);
+        radix_hist_kernel<<<grid, HIST_THREADS, 0, stream>>>(keys, n, begin_bit, npass, last_mask, d_hist_);
+        PSS_LAUNCH_CHECK();
+        radix_scan_kernel<<<npass, RADIX, 0, stream>>>(d_hist_, d_bin_base_, d_ctrl_, n);
+        PSS_LAUNCH_CHECK();
+    }
+    uint64_t *kin = keys, *kout = keys_alt;
+    uint32_t *vin = vals, *vout = vals_alt;
+    bool iota = iota_vals;
+    for (int p = 0; p < npass; ++p) {
+        const int shift     = begin_bit + p * RADIX_BITS;
+        const uint32_t mask = (p == npass - 1) ? last_mask : (uint32_t)(RADIX - 1);
+        PSS_CUDA_TRY(cudaMemsetAsync(d_tile_state_, 0, (size_t)tiles * RADIX * sizeof(uint32_t), stream));
+        const uint32_t *vals_arg = iota ? nullptr : vin;
+        const uint32_t *base_arg = d_bin_base_ + p * RADIX;
+        uint32_t n_arg = n, mask_arg = mask;
+        int shift_arg = shift, slot_arg = p;
+        void *args[] = {&kin, &kout, &vals_arg, &vout, &n_arg, &shift_arg, &mask_arg, &base_arg,
+                        &d_tile_state_, &d_ctrl_, &slot_arg};
+        PSS_CUDA_TRY(cudaLaunchKernel(pc.fn[iota ? 1 : 0][ballot_mode_ == 0 ? 0 : 1], dim3(tiles), dim3(pc.threads), args,
+                                      (size_t)pc.smem, stream));
+        count_launch();
+        iota = false;
+        std::swap(kin, kout);
+        std::swap(vin, vout);
+    }
+    *in_alt = (npass & 1) != 0;
     return PSS_OK;
 }
 

@@ -85,6 +85,7 @@ public:
     int  init(int device);
     int  ensure(int64_t n);  // workspace for up to n records
     void release();
+    void release_workspace();   // frees the tile-state array only (regrows on demand)
 
     // Sorts records by key bits [begin_bit, end_bit), stable.  iota_vals means the input
     // values are 0..n-1 and `vals` is only scratch (they are generated on the fly in the
@@ -107,7 +108,15 @@ public:
     int partition(uint64_t *keys, uint64_t *keys_alt, uint32_t n, int shift, uint32_t mask,
                   cudaStream_t stream, bool *in_alt);
 
+    // Same sort with no host round trip: every digit's pass runs (a constant digit costs a
+    // stable copy instead of being skipped) and lanes are matched with ballots.  Nothing is
+    // synchronised; *in_alt is known up front (odd number of digits).  The look-back
+    // watchdog flag is sticky until poll_error() / error_flag() is consulted.
+    int sort_async(uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, uint32_t *vals_alt,
+                   uint32_t n, int begin_bit, int end_bit, bool iota_vals, cudaStream_t stream, bool *in_alt);
+
     int poll_error(cudaStream_t stream);
+    const uint32_t *d_error_flag() const;   // device word, non-zero once a watchdog fired
 
     int device() const { return device_; }
 

@@ -378,6 +378,7 @@ rerank_apply_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
         if (tile_id > 0) {
             int64_t basep  = (int64_t)tile_id - 1;
             uint32_t spins = 0;
+            uint64_t t0 = 0;
             while (true) {
                 const int64_t q = basep - lane;
                 unsigned long long w0 = 2ull << 62, w1 = 2ull << 62;   // before tile 0: inclusive identity
@@ -394,7 +395,12 @@ rerank_apply_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
                 const uint32_t m_wait  = __ballot_sync(0xffffffffu, !ready) & need;
                 if (m_abort & need) { aborted = true; break; }
                 if (m_wait) {
-                    if (++spins > (1u << 22)) { aborted = true; break; }
+                    // wall-clock watchdog (warp-uniform: every lane evaluates the same values)
+                    if ((++spins & 0x3FFFu) == 0) {
+                        const uint64_t now = __shfl_sync(0xffffffffu, global_timer_ns(), 0);
+                        if (t0 == 0) t0 = now;
+                        else if (now - t0 > 30ull * 1000ull * 1000ull * 1000ull) { aborted = true; break; }
+                    }
                     continue;
                 }
                 Tup v = {0, 0, 0};
@@ -537,6 +543,19 @@ int SaBuilder::ensure_io(int64_t n) {
     return PSS_OK;
 }
 
+void SaBuilder::release_workspace() {
+    if (device_ < 0) return;
+    cudaSetDevice(device_);
+    cudaFree(keys_a_); cudaFree(keys_b_); cudaFree(vals_a_); cudaFree(vals_b_);
+    cudaFree(grp_); cudaFree(isa_); cudaFree(tile_aggr_);
+    cudaFree(d_text_); cudaFree(d_sa_);
+    keys_a_ = keys_b_ = nullptr; vals_a_ = vals_b_ = grp_ = isa_ = tile_aggr_ = nullptr;
+    d_text_ = nullptr; d_sa_ = nullptr;
+    cap_ = io_cap_ = 0;
+    stager_.release();
+    sorter_.release_workspace();
+}
+
 void SaBuilder::release() {
     if (device_ < 0) return;
     cudaSetDevice(device_);
@@ -544,12 +563,7 @@ void SaBuilder::release() {
     cudaFree(grp_); cudaFree(isa_); cudaFree(tile_aggr_); cudaFree(d_small_);
     cudaFree(d_text_); cudaFree(d_sa_);
     if (h_small_) cudaFreeHost(h_small_);
-    for (int i = 0; i < 2; ++i) {
-        if (stage_[i]) cudaFreeHost(stage_[i]);
-        if (stage_ev_[i]) cudaEventDestroy(stage_ev_[i]);
-        stage_[i] = nullptr;
-        stage_ev_[i] = nullptr;
-    }
+    stager_.release();
     if (ev_begin_) cudaEventDestroy(ev_begin_);
     if (ev_end_) cudaEventDestroy(ev_end_);
     if (stream_) cudaStreamDestroy(stream_);
@@ -716,12 +730,7 @@ int SaBuilder::build_device(const uint8_t *d_text, int32_t n, int32_t *d_sa, cud
     return PSS_OK;
 }
 
-// ---- host <-> device copies for callers with ordinary (pageable) memory -----------------------
-// A Rust/C host calls pss_libsais with plain heap buffers.  cudaMemcpy from/to pageable memory
-// runs at a fraction of the PCIe rate (one driver thread stages through a small pinned
-// buffer), and the 4n-byte suffix array is four times the text.  These helpers stage through
-// two pinned slices themselves and move the slices with several CPU threads while the DMA of
-// the next slice is in flight.
+// ---- host <-> device copies for callers with ordinary (pageable) memory (HostStager) --------------
 namespace {
 
 constexpr size_t STAGE_SLICE = 16u << 20;
@@ -759,11 +768,30 @@ int copy_threads() {
 
 }  // namespace
 
-int SaBuilder::staged_copy(void *dst, const void *src, size_t bytes, bool to_device) {
+void HostStager::release() {
+    for (int i = 0; i < 2; ++i) {
+        if (stage_[i]) cudaFreeHost(stage_[i]);
+        if (ev_[i]) cudaEventDestroy(ev_[i]);
+        stage_[i]   = nullptr;
+        ev_[i]      = nullptr;
+        pending_[i] = false;
+    }
+}
+
+int HostStager::copy(void *dst, const void *src, size_t bytes, bool to_device, cudaStream_t stream) {
+    if (bytes == 0) return PSS_OK;
+    const void *host = to_device ? src : dst;
+    if (bytes < STAGE_MIN || host_pointer_is_pinned(host)) {
+        PSS_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, stream));
+        // pageable + small: the runtime has staged the bytes on return; pinned: the caller's
+        // buffer must stay untouched until the stream reaches this point
+        if (!to_device) PSS_CUDA_TRY(cudaStreamSynchronize(stream));
+        return PSS_OK;
+    }
     if (!stage_[0]) {
         for (int i = 0; i < 2; ++i) {
             PSS_CUDA_TRY(cudaMallocHost(&stage_[i], STAGE_SLICE));
-            PSS_CUDA_TRY(cudaEventCreateWithFlags(&stage_ev_[i], cudaEventDisableTiming));
+            PSS_CUDA_TRY(cudaEventCreateWithFlags(&ev_[i], cudaEventDisableTiming));
         }
     }
     const int threads = copy_threads();
@@ -771,25 +799,35 @@ int SaBuilder::staged_copy(void *dst, const void *src, size_t bytes, bool to_dev
     const uint8_t *s = static_cast<const uint8_t *>(src);
     const size_t nsl = (bytes + STAGE_SLICE - 1) / STAGE_SLICE;
     auto len_of = [&](size_t i) { return std::min(STAGE_SLICE, bytes - i * STAGE_SLICE); };
+    auto wait_free = [&](int b) -> int {     // the DMA that last used bounce buffer b has finished
+        if (pending_[b]) {
+            PSS_CUDA_TRY(cudaEventSynchronize(ev_[b]));
+            pending_[b] = false;
+        }
+        return PSS_OK;
+    };
     if (to_device) {
         for (size_t i = 0; i < nsl; ++i) {
             const int b = (int)(i & 1);
-            if (i >= 2) PSS_CUDA_TRY(cudaEventSynchronize(stage_ev_[b]));   // slice i-2 has left the bounce buffer
+            PSS_TRY(wait_free(b));
             parallel_memcpy(static_cast<uint8_t *>(stage_[b]), s + i * STAGE_SLICE, len_of(i), threads);
-            PSS_CUDA_TRY(cudaMemcpyAsync(d + i * STAGE_SLICE, stage_[b], len_of(i), cudaMemcpyHostToDevice, stream_));
-            PSS_CUDA_TRY(cudaEventRecord(stage_ev_[b], stream_));
+            PSS_CUDA_TRY(cudaMemcpyAsync(d + i * STAGE_SLICE, stage_[b], len_of(i), cudaMemcpyHostToDevice, stream));
+            PSS_CUDA_TRY(cudaEventRecord(ev_[b], stream));
+            pending_[b] = true;
         }
-        return PSS_OK;   // completion is ordered on stream_
+        return PSS_OK;   // completion is ordered on `stream`
     }
     for (size_t i = 0; i <= nsl; ++i) {
         if (i < nsl) {
             const int b = (int)(i & 1);
-            PSS_CUDA_TRY(cudaMemcpyAsync(stage_[b], s + i * STAGE_SLICE, len_of(i), cudaMemcpyDeviceToHost, stream_));
-            PSS_CUDA_TRY(cudaEventRecord(stage_ev_[b], stream_));
+            PSS_TRY(wait_free(b));
+            PSS_CUDA_TRY(cudaMemcpyAsync(stage_[b], s + i * STAGE_SLICE, len_of(i), cudaMemcpyDeviceToHost, stream));
+            PSS_CUDA_TRY(cudaEventRecord(ev_[b], stream));
+            pending_[b] = true;
         }
         if (i >= 1) {   // while slice i is in flight, move slice i-1 out of its bounce buffer
             const int pb = (int)((i - 1) & 1);
-            PSS_CUDA_TRY(cudaEventSynchronize(stage_ev_[pb]));
+            PSS_TRY(wait_free(pb));
             parallel_memcpy(d + (i - 1) * STAGE_SLICE, static_cast<const uint8_t *>(stage_[pb]), len_of(i - 1), threads);
         }
     }
@@ -801,19 +839,9 @@ int SaBuilder::build_host(const uint8_t *h_text, int32_t n, int32_t *h_sa) {
     if (n == 0) return PSS_OK;
     PSS_CUDA_TRY(cudaSetDevice(device_));
     PSS_TRY(ensure_io(n));
-    const bool big = (size_t)n >= STAGE_MIN;
-    if (big && !host_pointer_is_pinned(h_text)) {
-        PSS_TRY(staged_copy(d_text_, h_text, (size_t)n, /*to_device=*/true));
-    } else {
-        PSS_CUDA_TRY(cudaMemcpyAsync(d_text_, h_text, (size_t)n, cudaMemcpyHostToDevice, stream_));
-    }
+    PSS_TRY(stager_.copy(d_text_, h_text, (size_t)n, /*to_device=*/true, stream_));
     PSS_TRY(build_device(d_text_, n, d_sa_, stream_));
-    if (big && !host_pointer_is_pinned(h_sa)) {
-        PSS_TRY(staged_copy(h_sa, d_sa_, (size_t)n * sizeof(int32_t), /*to_device=*/false));
-    } else {
-        PSS_CUDA_TRY(cudaMemcpyAsync(h_sa, d_sa_, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
-        PSS_CUDA_TRY(cudaStreamSynchronize(stream_));
-    }
+    PSS_TRY(stager_.copy(h_sa, d_sa_, (size_t)n * sizeof(int32_t), /*to_device=*/false, stream_));
     return PSS_OK;
 }
 

@@ -22,6 +22,29 @@
 
 namespace pss {
 
+// Host <-> device copies for callers with ordinary (pageable) memory.  A Rust/C host calls
+// pss_libsais with plain heap buffers; cudaMemcpy from/to pageable memory runs at a fraction
+// of the PCIe rate (one driver thread stages through a small pinned buffer), and the 4n-byte
+// suffix array is four times the text.  The stager bounces through two pinned slices itself
+// and moves the slices with several CPU threads while the DMA of the next one is in flight.
+// Pinned callers' buffers are copied directly.
+class HostStager {
+public:
+    HostStager() = default;
+    ~HostStager() { release(); }
+    HostStager(const HostStager &) = delete;
+    HostStager &operator=(const HostStager &) = delete;
+    // to_device: returns once the host buffer has been consumed; completion on the device is
+    // ordered on `stream`.  from device: complete (host buffer filled) on return.
+    int  copy(void *dst, const void *src, size_t bytes, bool to_device, cudaStream_t stream);
+    void release();
+
+private:
+    void       *stage_[2]   = {nullptr, nullptr};
+    cudaEvent_t ev_[2]      = {nullptr, nullptr};
+    bool        pending_[2] = {false, false};
+};
+
 class SaBuilder {
 public:
     SaBuilder() = default;
@@ -31,6 +54,7 @@ public:
 
     int  init(int device, int64_t max_n);
     void release();
+    void release_workspace();   // frees the sort workspace and I/O buffers (they regrow on demand)
 
     int build_device(const uint8_t *d_text, int32_t n, int32_t *d_sa, cudaStream_t stream);
     int build_host(const uint8_t *h_text, int32_t n, int32_t *h_sa);
@@ -48,7 +72,6 @@ public:
 
 private:
     int ensure(int64_t n);
-    int staged_copy(void *dst, const void *src, size_t bytes, bool to_device);
 
     int          device_   = -1;
     cudaStream_t stream_   = nullptr;
@@ -65,8 +88,7 @@ private:
     uint8_t     *d_text_   = nullptr;
     int32_t     *d_sa_     = nullptr;
     cudaEvent_t  ev_begin_ = nullptr, ev_end_ = nullptr;
-    void        *stage_[2]    = {nullptr, nullptr};   // pinned bounce slices for pageable callers
-    cudaEvent_t  stage_ev_[2] = {nullptr, nullptr};
+    HostStager   stager_;                              // pinned bounce slices for pageable callers
     bool         profiling_ = false;
     pss_build_stats stats_ = {};
     std::vector<pss_pass_stat> pass_stats_;

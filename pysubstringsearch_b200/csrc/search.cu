@@ -2,6 +2,7 @@
 #include "search.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 
@@ -75,11 +76,154 @@ bounds_kernel(const DeviceChunk *__restrict__ chunks, int nc, const uint8_t *__r
     if (pair >= npairs) return;
     const uint32_t q = pair / (uint32_t)nc, c = pair % (uint32_t)nc;
     uint32_t lb, cnt;
-    warp_bounds(chunks[c].text, chunks[c].sa, chunks[c].n, patterns + pat_off[q],
-                (uint32_t)(pat_off[q + 1] - pat_off[q]), lane, &lb, &cnt);
+    // a malformed offsets array (device callers) must not turn into a wild pattern length
+    const int64_t o0 = pat_off[q], o1 = pat_off[q + 1];
+    const uint32_t m = o1 > o0 ? (uint32_t)min(o1 - o0, (int64_t)0x7FFFFFFF) : 0u;
+    warp_bounds(chunks[c].text, chunks[c].sa, chunks[c].n, patterns + o0, m, lane, &lb, &cnt);
     if (lane == 0) {
         lb_out[pair]  = lb;
         cnt_out[pair] = cnt;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Single-CTA scans over per-pair arrays (npairs is small next to the hit count): thread t
+// owns a contiguous range, the partials are scanned in shared memory.
+// ------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 1024;
+
+// hit_off[p] = sum of cnt[0..p) (u32, wraps only when the batch is oversized, which the
+// u64 total reveals); hit_off[npairs] = total.
+__global__ void __launch_bounds__(SCAN_THREADS)
+hit_offsets_kernel(const uint32_t *__restrict__ cnt, uint32_t npairs, uint32_t *__restrict__ hit_off,
+                   unsigned long long *__restrict__ total_out) {
+    __shared__ unsigned long long s_part[SCAN_THREADS];
+    const uint32_t per = (npairs + SCAN_THREADS - 1) / SCAN_THREADS;
+    const uint32_t lo  = min(npairs, threadIdx.x * per), hi = min(npairs, lo + per);
+    unsigned long long sum = 0;
+    for (uint32_t p = lo; p < hi; ++p) sum += cnt[p];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < SCAN_THREADS; o <<= 1) {
+        unsigned long long y = threadIdx.x >= (uint32_t)o ? s_part[threadIdx.x - o] : 0ull;
+        __syncthreads();
+        s_part[threadIdx.x] += y;
+        __syncthreads();
+    }
+    unsigned long long run = s_part[threadIdx.x] - sum;
+    for (uint32_t p = lo; p < hi; ++p) {
+        hit_off[p] = (uint32_t)run;
+        run += cnt[p];
+    }
+    if (threadIdx.x == SCAN_THREADS - 1) {
+        hit_off[npairs] = (uint32_t)s_part[SCAN_THREADS - 1];
+        *total_out      = s_part[SCAN_THREADS - 1];
+    }
+}
+
+// pair_first[p] = output offset of pair p's first entry, 0xFFFFFFFF for pairs without hits
+// (written by compact_kernel).  entry_off[p] = base + entries before pair p = the first
+// offset of the next pair that has hits (suffix minimum), or the sub-batch total.
+__global__ void __launch_bounds__(SCAN_THREADS)
+entry_offsets_kernel(const uint32_t *__restrict__ pair_first, uint32_t np, const uint32_t *__restrict__ kept_total,
+                     uint32_t base, uint32_t *__restrict__ entry_off) {
+    __shared__ uint32_t s_part[SCAN_THREADS];
+    const uint32_t per = (np + SCAN_THREADS - 1) / SCAN_THREADS;
+    const uint32_t lo  = min(np, threadIdx.x * per), hi = min(np, lo + per);
+    uint32_t mn = 0xFFFFFFFFu;
+    for (uint32_t p = lo; p < hi; ++p) mn = min(mn, pair_first[p]);
+    s_part[threadIdx.x] = mn;
+    __syncthreads();
+    // suffix minimum over the partials (Hillis-Steele, looking right)
+    for (int o = 1; o < SCAN_THREADS; o <<= 1) {
+        uint32_t y = threadIdx.x + o < SCAN_THREADS ? s_part[threadIdx.x + o] : 0xFFFFFFFFu;
+        __syncthreads();
+        s_part[threadIdx.x] = min(s_part[threadIdx.x], y);
+        __syncthreads();
+    }
+    const uint32_t total = *kept_total;
+    uint32_t carry = threadIdx.x + 1 < SCAN_THREADS ? s_part[threadIdx.x + 1] : 0xFFFFFFFFu;
+    carry = min(carry, total);
+    for (uint32_t p = hi; p > lo; --p) {
+        carry = min(carry, pair_first[p - 1]);
+        entry_off[p - 1] = base + carry;
+    }
+    if (threadIdx.x == 0) entry_off[np] = base + total;
+}
+
+__global__ void __launch_bounds__(256)
+query_offsets_kernel(const uint32_t *__restrict__ entry_off, uint32_t nq, uint32_t nc, int64_t *__restrict__ query_off) {
+    const uint32_t q = blockIdx.x * 256 + threadIdx.x;
+    if (q <= nq) query_off[q] = (int64_t)entry_off[(size_t)q * nc];
+}
+
+// ------------------------------------------------------------------------------------
+// newline side index: sorted offsets of every '\n' of a chunk
+// ------------------------------------------------------------------------------------
+constexpr int NL_THREADS = 256;
+constexpr int NL_BYTES_PER_THREAD = 16;
+constexpr int NL_TILE = NL_THREADS * NL_BYTES_PER_THREAD;   // 4096 text bytes per CTA
+
+__device__ __forceinline__ uint32_t block_excl_sum_256(uint32_t v, uint32_t *s_warp, uint32_t *total) {
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += y;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t pre = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        uint32_t t = s_warp[w];
+        if ((uint32_t)w < warp) pre += t;
+        tot += t;
+    }
+    *total = tot;
+    __syncthreads();
+    return pre + incl - v;
+}
+
+// bit j of the result is set when byte j of the thread's 16-byte slice is '\n' (the text
+// buffer has 16 readable zero bytes past n, and its base is 256-byte aligned)
+__device__ __forceinline__ uint32_t newline_mask16(const uint8_t *__restrict__ text, uint32_t n, uint32_t at) {
+    if (at >= n) return 0;
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(text + at));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t eq = __vcmpeq4(w[k], 0x0A0A0A0Au);   // 0xFF per equal byte
+        m |= ((eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u)) << (4 * k);
+    }
+    const uint32_t left = n - at;
+    if (left < 16) m &= (1u << left) - 1u;
+    return m;
+}
+
+__global__ void __launch_bounds__(NL_THREADS)
+newline_count_kernel(const uint8_t *__restrict__ text, uint32_t n, uint32_t *__restrict__ tile_sum) {
+    __shared__ uint32_t s_warp[8];
+    const uint32_t at = blockIdx.x * NL_TILE + threadIdx.x * NL_BYTES_PER_THREAD;
+    uint32_t total;
+    (void)block_excl_sum_256(__popc(newline_mask16(text, n, at)), s_warp, &total);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(NL_THREADS)
+newline_fill_kernel(const uint8_t *__restrict__ text, uint32_t n, const uint32_t *__restrict__ tile_prefix,
+                    uint32_t *__restrict__ nl) {
+    __shared__ uint32_t s_warp[8];
+    const uint32_t at = blockIdx.x * NL_TILE + threadIdx.x * NL_BYTES_PER_THREAD;
+    uint32_t m = newline_mask16(text, n, at);
+    uint32_t total;
+    uint32_t o = tile_prefix[blockIdx.x] + block_excl_sum_256(__popc(m), s_warp, &total);
+    while (m) {
+        const int b = __ffs(m) - 1;
+        nl[o++] = at + b;
+        m &= m - 1;
     }
 }
 
@@ -101,47 +245,86 @@ __device__ __forceinline__ uint32_t ld_text_word(const uint8_t *text, uint32_t i
     return __ldg(reinterpret_cast<const uint32_t *>(text + i));
 }
 
-// first '\n' at or after pos (lib.rs:266-269; none → n - 1)
-__device__ __forceinline__ uint32_t next_newline(const uint8_t *__restrict__ text, uint32_t n, uint32_t pos) {
-    uint32_t i  = pos & ~3u;
-    uint32_t eq = __vcmpeq4(ld_text_word(text, i), 0x0A0A0A0Au) & (0xFFFFFFFFu << (8 * (pos & 3u)));
-    while (eq == 0) {
-        i += 4;
-        if (i >= n) return n - 1;
-        eq = __vcmpeq4(ld_text_word(text, i), 0x0A0A0A0Au);
-    }
-    uint32_t e = i + ((__ffs(eq) - 1) >> 3);
-    return e < n ? e : n - 1;
-}
+constexpr uint32_t SCAN_LIMIT = 64;   // bytes scanned each way before the newline index decides
 
-// 1 + last '\n' strictly before pos (lib.rs:270-273; none → 0)
-__device__ __forceinline__ uint32_t line_begin(const uint8_t *__restrict__ text, uint32_t pos) {
-    if (pos == 0) return 0;
-    const uint32_t q = pos - 1;
-    uint32_t i  = q & ~3u;
-    uint32_t eq = __vcmpeq4(ld_text_word(text, i), 0x0A0A0A0Au) & (0xFFFFFFFFu >> (8 * (3u - (q & 3u))));
-    while (eq == 0) {
-        if (i == 0) return 0;
-        i -= 4;
-        eq = __vcmpeq4(ld_text_word(text, i), 0x0A0A0A0Au);
+// Entry around text position pos: *b = 1 + last '\n' strictly before pos (none → 0,
+// lib.rs:270-273), *e = first '\n' at or after pos (none → n - 1, lib.rs:266-269).
+__device__ __forceinline__ void entry_bounds(const DeviceChunk &ch, uint32_t pos, uint32_t *b_out, uint32_t *e_out) {
+    const uint8_t *__restrict__ text = ch.text;
+    const uint32_t n = ch.n;
+    const bool bounded = ch.nl != nullptr;
+    // forward
+    bool     have_e = false;
+    uint32_t e = 0;
+    {
+        uint32_t i  = pos & ~3u;
+        uint32_t eq = __vcmpeq4(ld_text_word(text, i), 0x0A0A0A0Au) & (0xFFFFFFFFu << (8 * (pos & 3u)));
+        const uint32_t stop = bounded ? min(n, (pos & ~3u) + SCAN_LIMIT) : n;
+        while (eq == 0) {
+            i += 4;
+            if (i >= stop) break;
+            eq = __vcmpeq4(ld_text_word(text, i), 0x0A0A0A0Au);
+        }
+        if (eq) {
+            e = i + ((__ffs(eq) - 1) >> 3);
+            e = e < n ? e : n - 1;
+            have_e = true;
+        } else if (i >= n) {
+            e = n - 1;
+            have_e = true;
+        }
     }
-    return i + ((31 - __clz(eq)) >> 3) + 1;
+    // backward
+    bool     have_b = false;
+    uint32_t b = 0;
+    if (pos == 0) {
+        have_b = true;
+    } else {
+        const uint32_t q = pos - 1;
+        uint32_t i  = q & ~3u;
+        uint32_t eq = __vcmpeq4(ld_text_word(text, i), 0x0A0A0A0Au) & (0xFFFFFFFFu >> (8 * (3u - (q & 3u))));
+        const uint32_t stop = (bounded && i > SCAN_LIMIT) ? i - SCAN_LIMIT : 0u;
+        bool at_zero = false;
+        while (eq == 0) {
+            if (i == 0) { at_zero = true; break; }
+            if (i <= stop) break;
+            i -= 4;
+            eq = __vcmpeq4(ld_text_word(text, i), 0x0A0A0A0Au);
+        }
+        if (eq) {
+            b = i + ((31 - __clz(eq)) >> 3) + 1;
+            have_b = true;
+        } else if (at_zero) {
+            have_b = true;
+        }
+    }
+    if (!(have_e && have_b)) {
+        // long line: j = number of newlines before pos (first index with nl[j] >= pos)
+        uint32_t lo = 0, hi = ch.n_lines;
+        while (lo < hi) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (__ldg(ch.nl + mid) < pos) lo = mid + 1;
+            else hi = mid;
+        }
+        if (!have_e) e = lo < ch.n_lines ? __ldg(ch.nl + lo) : n - 1;
+        if (!have_b) b = lo > 0 ? __ldg(ch.nl + lo - 1) + 1 : 0u;
+    }
+    *b_out = b;
+    *e_out = e;
 }
 
 __global__ void __launch_bounds__(256)
 extract_kernel(const DeviceChunk *__restrict__ chunks, int nc, uint32_t pair_base, uint32_t npairs,
-               const uint32_t *__restrict__ hit_off, const uint32_t *__restrict__ lb, uint32_t nhits, int sbits,
-               uint64_t *__restrict__ keys, uint32_t *__restrict__ line_end) {
+               const uint32_t *__restrict__ hit_off, uint32_t hit_base, const uint32_t *__restrict__ lb, uint32_t nhits,
+               int sbits, uint64_t *__restrict__ keys, uint32_t *__restrict__ line_end) {
     const uint32_t f = blockIdx.x * 256 + threadIdx.x;
     if (f >= nhits) return;
-    const uint32_t p    = find_pair(hit_off, npairs, f);
+    const uint32_t p    = find_pair(hit_off, npairs, f + hit_base);
     const uint32_t pair = pair_base + p;
-    const uint32_t c    = pair % (uint32_t)nc;
-    const uint8_t *text = chunks[c].text;
-    const uint32_t n    = chunks[c].n;
-    const uint32_t pos  = (uint32_t)__ldg(chunks[c].sa + __ldg(lb + pair) + (f - __ldg(hit_off + p)));
-    const uint32_t e    = next_newline(text, n, pos);
-    const uint32_t b    = line_begin(text, pos);
+    const DeviceChunk ch = chunks[pair % (uint32_t)nc];
+    const uint32_t pos  = (uint32_t)__ldg(ch.sa + __ldg(lb + pair) + (f + hit_base - __ldg(hit_off + p)));
+    uint32_t b, e;
+    entry_bounds(ch, pos, &b, &e);
     keys[f]     = ((uint64_t)p << sbits) | b;
     line_end[f] = e;
 }
@@ -164,28 +347,6 @@ constexpr int CP_THREADS = 256;
 constexpr int CP_IPT     = 8;
 constexpr int CP_TILE    = CP_THREADS * CP_IPT;
 
-__device__ __forceinline__ uint32_t block_excl_sum(uint32_t v, uint32_t *s_warp, uint32_t *total) {
-    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    uint32_t incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (uint32_t)o) incl += y;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    uint32_t pre = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < CP_THREADS / 32; ++w) {
-        uint32_t t = s_warp[w];
-        if ((uint32_t)w < warp) pre += t;
-        tot += t;
-    }
-    *total = tot;
-    __syncthreads();
-    return pre + incl - v;
-}
-
 __global__ void __launch_bounds__(CP_THREADS)
 flag_reduce_kernel(const uint32_t *__restrict__ flag, uint32_t nhits, uint32_t *__restrict__ tile_sum) {
     __shared__ uint32_t s_warp[CP_THREADS / 32];
@@ -195,21 +356,21 @@ flag_reduce_kernel(const uint32_t *__restrict__ flag, uint32_t nhits, uint32_t *
     for (int e = 0; e < CP_IPT; ++e)
         if (base + e < nhits) c += flag[base + e] >> 31;
     uint32_t total;
-    (void)block_excl_sum(c, s_warp, &total);
+    (void)block_excl_sum_256(c, s_warp, &total);
     if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(SCAN_THREADS)
 tile_scan_kernel(uint32_t *__restrict__ tile_sum, uint32_t tiles, uint32_t *__restrict__ total_out) {
-    __shared__ uint32_t s_part[1024];
-    const uint32_t per = (tiles + 1023) / 1024;
+    __shared__ uint32_t s_part[SCAN_THREADS];
+    const uint32_t per = (tiles + SCAN_THREADS - 1) / SCAN_THREADS;
     const uint32_t lo  = min(tiles, threadIdx.x * per), hi = min(tiles, lo + per);
     uint32_t sum = 0;
     for (uint32_t t = lo; t < hi; ++t) sum += tile_sum[t];
     s_part[threadIdx.x] = sum;
     __syncthreads();
     // Hillis-Steele over 1024 partials
-    for (int o = 1; o < 1024; o <<= 1) {
+    for (int o = 1; o < SCAN_THREADS; o <<= 1) {
         uint32_t y = threadIdx.x >= (uint32_t)o ? s_part[threadIdx.x - o] : 0u;
         __syncthreads();
         s_part[threadIdx.x] += y;
@@ -221,14 +382,14 @@ tile_scan_kernel(uint32_t *__restrict__ tile_sum, uint32_t tiles, uint32_t *__re
         tile_sum[t] = run;
         run += v;
     }
-    if (threadIdx.x == 1023) *total_out = s_part[1023];
+    if (threadIdx.x == SCAN_THREADS - 1) *total_out = s_part[SCAN_THREADS - 1];
 }
 
 __global__ void __launch_bounds__(CP_THREADS)
 compact_kernel(const uint32_t *__restrict__ flag, const uint32_t *__restrict__ line_end,
-               const uint32_t *__restrict__ tile_prefix, const uint32_t *__restrict__ hit_off,
+               const uint32_t *__restrict__ tile_prefix, const uint32_t *__restrict__ hit_off, uint32_t hit_base,
                const DeviceChunk *__restrict__ chunks, int nc, uint32_t pair_base, uint32_t npairs, uint32_t nhits,
-               uint32_t *__restrict__ pair_first, int32_t *__restrict__ out_query, int32_t *__restrict__ out_chunk,
+               uint32_t *__restrict__ pair_first, int32_t *__restrict__ out_chunk,
                uint32_t *__restrict__ out_start, uint32_t *__restrict__ out_end) {
     __shared__ uint32_t s_warp[CP_THREADS / 32];
     const uint32_t base = blockIdx.x * CP_TILE + threadIdx.x * CP_IPT;
@@ -240,19 +401,17 @@ compact_kernel(const uint32_t *__restrict__ flag, const uint32_t *__restrict__ l
         c += fl[e] >> 31;
     }
     uint32_t total;
-    uint32_t o = block_excl_sum(c, s_warp, &total) + tile_prefix[blockIdx.x];
+    uint32_t o = block_excl_sum_256(c, s_warp, &total) + tile_prefix[blockIdx.x];
     if (base >= nhits) return;
-    uint32_t p = find_pair(hit_off, npairs, base);
+    uint32_t p = find_pair(hit_off, npairs, base + hit_base);
 #pragma unroll
     for (int e = 0; e < CP_IPT; ++e) {
         const uint32_t f = base + e;
         if (f >= nhits) break;
-        while (f >= __ldg(hit_off + p + 1)) ++p;           // skips pairs without hits
-        if (f == __ldg(hit_off + p)) pair_first[p] = o;    // first hit of pair p: its output offset
+        while (f + hit_base >= __ldg(hit_off + p + 1)) ++p;           // skips pairs without hits
+        if (f + hit_base == __ldg(hit_off + p)) pair_first[p] = o;    // first hit of pair p: its output offset
         if (fl[e] >> 31) {
-            const uint32_t pair = pair_base + p;
-            if (out_query) out_query[o] = (int32_t)(pair / (uint32_t)nc);
-            if (out_chunk) out_chunk[o] = chunks[pair % (uint32_t)nc].global_id;
+            out_chunk[o] = chunks[(pair_base + p) % (uint32_t)nc].global_id;
             out_start[o] = fl[e] & 0x7FFFFFFFu;
             out_end[o]   = line_end[f];
             ++o;
@@ -260,26 +419,29 @@ compact_kernel(const uint32_t *__restrict__ flag, const uint32_t *__restrict__ l
     }
 }
 
-
 // ------------------------------------------------------------------------------------
-// Small-batch path: one CTA answers a handful of (query, chunk) pairs end to end — bounds,
-// extraction, dedup (bitonic sort in shared memory) and compaction — so that a single
-// `Reader.search` costs one kernel launch and one device→host copy instead of ~15 launches.
-// Falls back (status = 1) when the pairs have more than SMALL_CAP matching suffixes.
+// Small-batch path: ONE launch answers a handful of (query, chunk) pairs end to end.
+// CTA p finds pair p's SA range with two concurrent 512-ary searches (lower bound in warps
+// 0-15, upper bound in warps 16-31: 4 rounds of independent probes at n = 2^29 instead of
+// 2 x 29 dependent ones); the last CTA to finish extracts the entries of all pairs, dedups
+// them with a bitonic sort in shared memory and writes header + tuples to `out`, which is
+// mapped pinned host memory: the host sees the result without a copy or a stream sync.
+// status = 1 when the pairs have more than SMALL_CAP matching suffixes (general path).
 // ------------------------------------------------------------------------------------
-constexpr int SMALL_THREADS   = 1024;
-constexpr int SMALL_CAP       = 8192;   // matching suffixes handled in shared memory
-constexpr int SMALL_MAX_PAIRS = 64;
+constexpr int SMALL_THREADS = 1024;
+constexpr int SMALL_CAP     = 8192;   // matching suffixes handled in shared memory
 
 struct SmallHeader {
+    uint32_t seq;         // written last: the host polls it
     uint32_t status;      // 0 = answered, 1 = too many hits (use the general path)
     uint32_t n_hits;
     uint32_t n_entries;
-    uint32_t reserved;
-    uint32_t pair_entries[SMALL_MAX_PAIRS];
+    uint32_t entry_off[SMALL_MAX_PAIRS + 1];
+    uint32_t pad[3];
+    long long query_off[SMALL_MAX_QUERIES + 1];
 };
-// Packed result buffer: header, then query / chunk / start / end arrays of SMALL_CAP each.
-constexpr size_t SMALL_OUT_BYTES = sizeof(SmallHeader) + 4 * (size_t)SMALL_CAP * sizeof(uint32_t);
+// Result block: header, then chunk / start / end arrays of SMALL_CAP each.
+constexpr size_t SMALL_OUT_BYTES = sizeof(SmallHeader) + 3 * (size_t)SMALL_CAP * sizeof(uint32_t);
 
 struct SmallSmem {
     uint64_t key[SMALL_CAP];       // (pair << 43) | (entry start << 13) | hit index
@@ -288,37 +450,106 @@ struct SmallSmem {
     uint32_t lb[SMALL_MAX_PAIRS], cnt[SMALL_MAX_PAIRS], off[SMALL_MAX_PAIRS + 1], pair_entries[SMALL_MAX_PAIRS];
     uint32_t warp_sum[SMALL_THREADS / 32];
     uint32_t total;
+    uint32_t count[2];
+    uint32_t is_last;
+    uint8_t  pat[SMALL_PAT_BYTES];
 };
 
+// One thread compares the suffix at s with P: -1 / 0 (P is a prefix) / +1, as cmp_suffix.
+__device__ __forceinline__ int cmp_suffix_thread(const uint8_t *__restrict__ text, uint32_t n, uint32_t s,
+                                                 const uint8_t *P, uint32_t m) {
+    const uint32_t avail = n - s;
+    for (uint32_t b = 0; b < m; ++b) {
+        if (b >= avail) return -1;
+        const uint32_t tc = __ldg(text + s + b), pc = P[b];
+        if (tc != pc) return tc < pc ? -1 : 1;
+    }
+    return 0;
+}
+
 __global__ void __launch_bounds__(SMALL_THREADS, 1)
-small_search_kernel(const DeviceChunk *__restrict__ chunks, int nc, const uint8_t *__restrict__ patterns,
-                    const int64_t *__restrict__ pat_off, uint32_t npairs, uint32_t *__restrict__ lb_out,
-                    uint32_t *__restrict__ cnt_out, unsigned char *__restrict__ out) {
+small_search_kernel(const DeviceChunk *__restrict__ chunks, int nc, const __grid_constant__ SmallPatterns pats,
+                    uint32_t npairs, uint32_t seq, uint32_t *__restrict__ lb_out, uint32_t *__restrict__ cnt_out,
+                    uint32_t *__restrict__ ticket, unsigned char *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmallSmem &s = *reinterpret_cast<SmallSmem *>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
-    SmallHeader *hdr   = reinterpret_cast<SmallHeader *>(out);
-    int32_t  *o_query  = reinterpret_cast<int32_t *>(out + sizeof(SmallHeader));
-    int32_t  *o_chunk  = o_query + SMALL_CAP;
-    uint32_t *o_start  = reinterpret_cast<uint32_t *>(o_chunk + SMALL_CAP);
-    uint32_t *o_end    = o_start + SMALL_CAP;
 
-    // ---- bounds: one warp per pair (same search as bounds_kernel) -------------------------------
-    for (uint32_t pair = warp; pair < npairs; pair += SMALL_THREADS / 32) {
+    // ---- phase 1: this CTA's pair -------------------------------------------------------
+    {
+        const uint32_t pair = blockIdx.x;
         const uint32_t q = pair / (uint32_t)nc, c = pair % (uint32_t)nc;
-        uint32_t lb, cnt;
-        warp_bounds(chunks[c].text, chunks[c].sa, chunks[c].n, patterns + pat_off[q],
-                    (uint32_t)(pat_off[q + 1] - pat_off[q]), lane, &lb, &cnt);
-        if (lane == 0) {
-            s.lb[pair] = lb;
-            s.cnt[pair] = cnt;
-            lb_out[pair] = lb;
-            cnt_out[pair] = cnt;
+        const uint32_t m = pats.off[q + 1] - pats.off[q];
+        for (uint32_t i = tid; i < m; i += SMALL_THREADS) s.pat[i] = pats.bytes[pats.off[q] + i];
+        if (tid < 2) s.count[tid] = 0;
+        __syncthreads();
+        const uint8_t *__restrict__ text = chunks[c].text;
+        const int32_t *__restrict__ sa   = chunks[c].sa;
+        const uint32_t n = chunks[c].n;
+        constexpr uint32_t T = SMALL_THREADS / 2;
+        const uint32_t which = tid / T;        // 0: lower bound (first slot with cmp >= 0), 1: upper (first with cmp > 0)
+        const uint32_t t     = tid % T;
+        uint32_t lo = 0, hi = n;               // the answer lies in [lo, hi]
+        while (true) {                         // both halves iterate in lockstep (block barriers)
+            const uint32_t R = hi - lo;
+            bool below = false;                // predicate "boundary is past my pivot"
+            uint32_t step = 1, pivots = 0;
+            if (R > 0) {
+                step   = (R + T - 1) / T;
+                pivots = (R + step - 1) / step;            // <= T
+                if (t < pivots) {
+                    const int cmp = cmp_suffix_thread(text, n, (uint32_t)__ldg(sa + lo + t * step), s.pat, m);
+                    below = which == 0 ? (cmp < 0) : (cmp <= 0);
+                }
+            }
+            const uint32_t votes = __popc(__ballot_sync(0xffffffffu, below));
+            if (lane == 0 && votes) atomicAdd(&s.count[which], votes);
+            __syncthreads();
+            const uint32_t c_true = s.count[which];
+            __syncthreads();
+            if (tid < 2) s.count[tid] = 0;
+            if (R > 0) {
+                // pivots 0..c_true-1 are below the boundary, pivot c_true (if any) is not:
+                // the range shrinks to fewer than `step` slots; step == 1 ends the search
+                if (c_true == 0) {
+                    hi = lo;                   // pivot 0 is the slot lo itself
+                } else {
+                    if (c_true < pivots) hi = lo + c_true * step;
+                    lo = lo + (c_true - 1) * step + 1;
+                }
+            }
+            // uniform exit: both searches must have converged (also orders the reset of the
+            // counters before the next round's votes)
+            if (__syncthreads_and(hi == lo ? 1 : 0)) break;
         }
+        if (t == 0) s.lb[which] = lo;          // reuse s.lb[0..1] as scratch for the two boundaries
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t lbv = s.lb[0], ubv = s.lb[1];
+            lb_out[pair]  = lbv;
+            cnt_out[pair] = ubv > lbv ? ubv - lbv : 0u;
+            __threadfence();
+            const uint32_t prev = atomicAdd(ticket, 1u);
+            s.is_last = (prev == npairs - 1) ? 1u : 0u;
+        }
+        __syncthreads();
+        if (!s.is_last) return;
+        __threadfence();
+    }
+
+    // ---- phase 2 (last CTA): extraction, dedup, compaction for all pairs ----------------------
+    SmallHeader *hdr  = reinterpret_cast<SmallHeader *>(out);
+    int32_t  *o_chunk = reinterpret_cast<int32_t *>(out + sizeof(SmallHeader));
+    uint32_t *o_start = reinterpret_cast<uint32_t *>(o_chunk + SMALL_CAP);
+    uint32_t *o_end   = o_start + SMALL_CAP;
+    if (tid < npairs) {
+        s.lb[tid]  = ld_volatile_u32(lb_out + tid);
+        s.cnt[tid] = ld_volatile_u32(cnt_out + tid);
     }
     if (tid < SMALL_MAX_PAIRS) s.pair_entries[tid] = 0;
     __syncthreads();
     if (tid == 0) {
+        *ticket = 0;                            // ready for the next launch
         uint64_t run = 0;
         for (uint32_t p = 0; p < npairs; ++p) {
             s.off[p] = (uint32_t)min(run, (uint64_t)0xFFFFFFFFu);
@@ -330,32 +561,35 @@ small_search_kernel(const DeviceChunk *__restrict__ chunks, int nc, const uint8_
     __syncthreads();
     const uint32_t H = s.total;
     if (H > SMALL_CAP) {
-        if (tid == 0) { hdr->status = 1; hdr->n_hits = H; hdr->n_entries = 0; }
+        if (tid == 0) {
+            hdr->status = 1; hdr->n_hits = H; hdr->n_entries = 0;
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t *>(&hdr->seq) = seq;
+        }
         return;
     }
     uint32_t P2 = 1;
     while (P2 < H) P2 <<= 1;
 
-    // ---- extract: entry boundaries of every matching suffix ---------------------------------
     for (uint32_t f = tid; f < P2; f += SMALL_THREADS) {
         uint64_t key = ~0ull;
         if (f < H) {
             uint32_t p = 0;
             while (s.off[p + 1] <= f) ++p;
-            const uint32_t c    = p % (uint32_t)nc;
-            const uint8_t *text = chunks[c].text;
-            const uint32_t n    = chunks[c].n;
-            const uint32_t pos  = (uint32_t)__ldg(chunks[c].sa + s.lb[p] + (f - s.off[p]));
-            s.end[f]   = next_newline(text, n, pos);
+            const DeviceChunk ch = chunks[p % (uint32_t)nc];
+            const uint32_t pos   = (uint32_t)__ldg(ch.sa + s.lb[p] + (f - s.off[p]));
+            uint32_t b, e;
+            entry_bounds(ch, pos, &b, &e);
+            s.end[f]   = e;
             s.start[f] = 0;
-            key = ((uint64_t)p << 43) | ((uint64_t)line_begin(text, pos) << 13) | f;
+            key = ((uint64_t)p << 43) | ((uint64_t)b << 13) | f;
         }
         s.key[f] = key;
     }
     __syncthreads();
 
-    // ---- dedup: bitonic sort by (pair, entry start, hit index); the head of every
-    //      (pair, entry start) run is the entry's first hit in SA order -------------------------
+    // bitonic sort by (pair, entry start, hit index); the head of every (pair, entry start)
+    // run is the entry's first hit in SA order
     for (uint32_t k = 2; k <= P2; k <<= 1) {
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
             for (uint32_t i = tid; i < P2; i += SMALL_THREADS) {
@@ -375,7 +609,7 @@ small_search_kernel(const DeviceChunk *__restrict__ chunks, int nc, const uint8_
     }
     __syncthreads();
 
-    // ---- compaction in hit order = (query, chunk, SA order) -------------------------------------
+    // compaction in hit order = (query, chunk, SA order)
     constexpr int PER = SMALL_CAP / SMALL_THREADS;
     const uint32_t base = tid * PER;
     uint32_t kept = 0;
@@ -407,7 +641,6 @@ small_search_kernel(const DeviceChunk *__restrict__ chunks, int nc, const uint8_
             while (s.off[p + 1] <= f) ++p;
             const uint32_t v = s.start[f];
             if (v >> 31) {
-                o_query[o] = (int32_t)(p / (uint32_t)nc);
                 o_chunk[o] = chunks[p % (uint32_t)nc].global_id;
                 o_start[o] = v & 0x7FFFFFFFu;
                 o_end[o]   = s.end[f];
@@ -417,8 +650,22 @@ small_search_kernel(const DeviceChunk *__restrict__ chunks, int nc, const uint8_
         }
     }
     __syncthreads();
-    if (tid < SMALL_MAX_PAIRS) hdr->pair_entries[tid] = s.pair_entries[tid];
-    if (tid == 0) { hdr->status = 0; hdr->n_hits = H; hdr->n_entries = tot; }
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (uint32_t p = 0; p < npairs; ++p) {
+            if (p % (uint32_t)nc == 0) hdr->query_off[p / (uint32_t)nc] = run;
+            hdr->entry_off[p] = run;
+            run += s.pair_entries[p];
+        }
+        hdr->entry_off[npairs] = run;
+        hdr->query_off[npairs / (uint32_t)nc] = run;
+        hdr->status = 0; hdr->n_hits = H; hdr->n_entries = tot;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence_system();                 // tuples + header fields are visible to the host first
+        *reinterpret_cast<volatile uint32_t *>(&hdr->seq) = seq;
+    }
 }
 
 }  // namespace
@@ -426,22 +673,6 @@ small_search_kernel(const DeviceChunk *__restrict__ chunks, int nc, const uint8_
 // ------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------
-int SearchSink::deliver_host(int64_t count, const int32_t *q, const int32_t *c, const uint32_t *s, const uint32_t *e,
-                             cudaStream_t st) {
-    int32_t *dq = nullptr, *dc = nullptr;
-    uint32_t *ds = nullptr, *de = nullptr;
-    PSS_TRY(reserve(count, &dq, &dc, &ds, &de));
-    if (count) {
-        if (dq) PSS_CUDA_TRY(cudaMemcpyAsync(dq, q, count * 4, cudaMemcpyHostToDevice, st));
-        if (dc) PSS_CUDA_TRY(cudaMemcpyAsync(dc, c, count * 4, cudaMemcpyHostToDevice, st));
-        PSS_CUDA_TRY(cudaMemcpyAsync(ds, s, count * 4, cudaMemcpyHostToDevice, st));
-        PSS_CUDA_TRY(cudaMemcpyAsync(de, e, count * 4, cudaMemcpyHostToDevice, st));
-    }
-    PSS_TRY(commit(count, st));
-    PSS_CUDA_TRY(cudaStreamSynchronize(st));
-    return PSS_OK;
-}
-
 int Searcher::init(int device) {
     if (device_ >= 0) return PSS_OK;
     if (device < 0) device = default_device();
@@ -454,15 +685,16 @@ int Searcher::init(int device) {
     PSS_CUDA_TRY(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     for (auto &e : ev_) PSS_CUDA_TRY(cudaEventCreate(&e));
     PSS_CUDA_TRY(cudaMalloc(&d_scalar_, 16 * sizeof(uint32_t)));
+    PSS_CUDA_TRY(cudaMemset(d_scalar_, 0, 16 * sizeof(uint32_t)));
     PSS_CUDA_TRY(cudaMallocHost(&h_scalar_, 16 * sizeof(uint32_t)));
-    PSS_CUDA_TRY(cudaMalloc(&d_small_out_, SMALL_OUT_BYTES));
-    PSS_CUDA_TRY(cudaMemset(d_small_out_, 0, SMALL_OUT_BYTES));   // the whole block is copied back every call
-    PSS_CUDA_TRY(cudaMallocHost(&h_small_out_, SMALL_OUT_BYTES));
+    PSS_CUDA_TRY(cudaHostAlloc(&h_small_out_, SMALL_OUT_BYTES, cudaHostAllocMapped));
+    std::memset(h_small_out_, 0, SMALL_OUT_BYTES);
     PSS_CUDA_TRY(cudaFuncSetAttribute(small_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(SmallSmem)));
     small_path_ = true;
     if (const char *e = std::getenv("PSS_SMALL_PATH")) small_path_ = std::atoi(e) != 0;
     PSS_TRY(sorter_.init(device_));
+    PSS_TRY(ensure_pairs(SMALL_MAX_PAIRS, SMALL_MAX_QUERIES));
     return PSS_OK;
 }
 
@@ -471,28 +703,30 @@ void Searcher::release() {
     cudaSetDevice(device_);
     cudaFree(d_chunks_);
     cudaFree(d_lb_); cudaFree(d_cnt_); cudaFree(d_hit_off_); cudaFree(d_pair_first_);
-    if (h_lb_) cudaFreeHost(h_lb_);
+    cudaFree(d_entry_off_); cudaFree(d_query_off_);
     if (h_cnt_) cudaFreeHost(h_cnt_);
     if (h_hit_off_) cudaFreeHost(h_hit_off_);
-    if (h_pair_first_) cudaFreeHost(h_pair_first_);
     cudaFree(d_keys_); cudaFree(d_keys_alt_); cudaFree(d_vals_); cudaFree(d_vals_alt_);
     cudaFree(d_end_); cudaFree(d_flag_); cudaFree(d_tile_sum_); cudaFree(d_scalar_);
-    cudaFree(d_small_out_);
+    cudaFree(d_out_chunk_); cudaFree(d_out_start_); cudaFree(d_out_end_);
     if (h_small_out_) cudaFreeHost(h_small_out_);
-    d_small_out_ = h_small_out_ = nullptr;
     if (h_scalar_) cudaFreeHost(h_scalar_);
     for (auto &e : ev_)
         if (e) cudaEventDestroy(e);
     if (stream_) cudaStreamDestroy(stream_);
     sorter_.release();
     d_chunks_ = nullptr;
-    d_lb_ = d_cnt_ = d_hit_off_ = d_pair_first_ = nullptr;
-    h_lb_ = h_cnt_ = h_hit_off_ = h_pair_first_ = nullptr;
+    d_lb_ = d_cnt_ = d_hit_off_ = d_pair_first_ = d_entry_off_ = nullptr;
+    d_query_off_ = nullptr;
+    h_cnt_ = h_hit_off_ = nullptr;
     d_keys_ = d_keys_alt_ = nullptr;
     d_vals_ = d_vals_alt_ = d_end_ = d_flag_ = d_tile_sum_ = d_scalar_ = h_scalar_ = nullptr;
+    d_out_chunk_ = nullptr;
+    d_out_start_ = d_out_end_ = nullptr;
+    h_small_out_ = nullptr;
     for (auto &e : ev_) e = nullptr;
     stream_ = nullptr;
-    pair_cap_ = hit_cap_ = 0;
+    pair_cap_ = query_cap_ = hit_cap_ = out_cap_ = 0;
     chunks_.clear();
     device_ = -1;
 }
@@ -509,26 +743,62 @@ int Searcher::set_chunks(const std::vector<DeviceChunk> &chunks) {
     return PSS_OK;
 }
 
-int Searcher::ensure_pairs(int64_t npairs) {
-    if (npairs <= pair_cap_) return PSS_OK;
-    cudaFree(d_lb_); cudaFree(d_cnt_); cudaFree(d_hit_off_); cudaFree(d_pair_first_);
-    if (h_lb_) cudaFreeHost(h_lb_);
-    if (h_cnt_) cudaFreeHost(h_cnt_);
-    if (h_hit_off_) cudaFreeHost(h_hit_off_);
-    if (h_pair_first_) cudaFreeHost(h_pair_first_);
-    d_lb_ = d_cnt_ = d_hit_off_ = d_pair_first_ = nullptr;
-    h_lb_ = h_cnt_ = h_hit_off_ = h_pair_first_ = nullptr;
-    pair_cap_ = 0;
-    int64_t cap = std::max<int64_t>(npairs, 1024);
-    PSS_CUDA_TRY(cudaMalloc(&d_lb_, cap * sizeof(uint32_t)));
-    PSS_CUDA_TRY(cudaMalloc(&d_cnt_, cap * sizeof(uint32_t)));
-    PSS_CUDA_TRY(cudaMalloc(&d_hit_off_, (cap + 1) * sizeof(uint32_t)));
-    PSS_CUDA_TRY(cudaMalloc(&d_pair_first_, cap * sizeof(uint32_t)));
-    PSS_CUDA_TRY(cudaMallocHost(&h_lb_, cap * sizeof(uint32_t)));
-    PSS_CUDA_TRY(cudaMallocHost(&h_cnt_, cap * sizeof(uint32_t)));
-    PSS_CUDA_TRY(cudaMallocHost(&h_hit_off_, (cap + 1) * sizeof(uint32_t)));
-    PSS_CUDA_TRY(cudaMallocHost(&h_pair_first_, cap * sizeof(uint32_t)));
-    pair_cap_ = cap;
+int Searcher::build_newline_index(const uint8_t *d_text, uint32_t n, uint32_t **d_nl, uint32_t *n_lines) {
+    *d_nl = nullptr;
+    *n_lines = 0;
+    if (n == 0) return PSS_OK;
+    PSS_CUDA_TRY(cudaSetDevice(device_));
+    if (reinterpret_cast<uintptr_t>(d_text) & 15) return fail(PSS_ERR_ARG, "chunk text must be 16-byte aligned on the device");
+    const uint32_t tiles = (uint32_t)div_up(n, NL_TILE);
+    uint32_t *d_tiles = nullptr;
+    PSS_CUDA_TRY(cudaMalloc(&d_tiles, (size_t)tiles * sizeof(uint32_t)));
+    struct Free { uint32_t *p; ~Free() { cudaFree(p); } } guard{d_tiles};
+    newline_count_kernel<<<tiles, NL_THREADS, 0, stream_>>>(d_text, n, d_tiles);
+    PSS_LAUNCH_CHECK();
+    tile_scan_kernel<<<1, SCAN_THREADS, 0, stream_>>>(d_tiles, tiles, d_scalar_ + 4);
+    PSS_LAUNCH_CHECK();
+    PSS_CUDA_TRY(cudaMemcpyAsync(h_scalar_ + 4, d_scalar_ + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
+    PSS_CUDA_TRY(cudaStreamSynchronize(stream_));
+    const uint32_t L = h_scalar_[4];
+    uint32_t *nl = nullptr;
+    PSS_CUDA_TRY(cudaMalloc(&nl, (size_t)std::max<uint32_t>(L, 1) * sizeof(uint32_t)));
+    newline_fill_kernel<<<tiles, NL_THREADS, 0, stream_>>>(d_text, n, d_tiles, nl);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
+    if (e != cudaSuccess) {
+        cudaFree(nl);
+        return fail(PSS_ERR_CUDA, std::string("newline index: ") + cudaGetErrorString(e));
+    }
+    *d_nl = nl;
+    *n_lines = L;
+    return PSS_OK;
+}
+
+int Searcher::ensure_pairs(int64_t npairs, int64_t nq) {
+    if (npairs > pair_cap_) {
+        cudaFree(d_lb_); cudaFree(d_cnt_); cudaFree(d_hit_off_); cudaFree(d_pair_first_); cudaFree(d_entry_off_);
+        if (h_cnt_) cudaFreeHost(h_cnt_);
+        if (h_hit_off_) cudaFreeHost(h_hit_off_);
+        d_lb_ = d_cnt_ = d_hit_off_ = d_pair_first_ = d_entry_off_ = nullptr;
+        h_cnt_ = h_hit_off_ = nullptr;
+        pair_cap_ = 0;
+        int64_t cap = std::max<int64_t>(npairs + npairs / 4, 1024);
+        PSS_CUDA_TRY(cudaMalloc(&d_lb_, cap * sizeof(uint32_t)));
+        PSS_CUDA_TRY(cudaMalloc(&d_cnt_, cap * sizeof(uint32_t)));
+        PSS_CUDA_TRY(cudaMalloc(&d_hit_off_, (cap + 1) * sizeof(uint32_t)));
+        PSS_CUDA_TRY(cudaMalloc(&d_pair_first_, cap * sizeof(uint32_t)));
+        PSS_CUDA_TRY(cudaMalloc(&d_entry_off_, (cap + 1) * sizeof(uint32_t)));
+        pair_cap_ = cap;
+    }
+    if (nq > query_cap_) {
+        cudaFree(d_query_off_);
+        d_query_off_ = nullptr;
+        query_cap_ = 0;
+        int64_t cap = std::max<int64_t>(nq + nq / 4, 1024);
+        PSS_CUDA_TRY(cudaMalloc(&d_query_off_, (cap + 1) * sizeof(int64_t)));
+        query_cap_ = cap;
+    }
     return PSS_OK;
 }
 
@@ -553,104 +823,182 @@ int Searcher::ensure_hits(int64_t nhits) {
     return PSS_OK;
 }
 
-int Searcher::search(const uint8_t *d_patterns, const int64_t *d_offsets, int32_t nq, cudaStream_t stream,
-                     SearchSink *sink, int64_t *per_pair_count, int64_t *n_hits, SearchTimes *times) {
+// Output arrays for `entries` tuples; what is already there is kept (sub-batches append).
+int Searcher::ensure_out(int64_t entries, cudaStream_t s) {
+    if (entries <= out_cap_) return PSS_OK;
+    int64_t cap = std::max<int64_t>(entries + entries / 4, 1 << 16);
+    int32_t  *nc = nullptr;
+    uint32_t *ns = nullptr, *ne = nullptr;
+    PSS_CUDA_TRY(cudaMalloc(&nc, cap * sizeof(int32_t)));
+    PSS_CUDA_TRY(cudaMalloc(&ns, cap * sizeof(uint32_t)));
+    PSS_CUDA_TRY(cudaMalloc(&ne, cap * sizeof(uint32_t)));
+    if (out_cap_) {
+        PSS_CUDA_TRY(cudaMemcpyAsync(nc, d_out_chunk_, out_cap_ * 4, cudaMemcpyDeviceToDevice, s));
+        PSS_CUDA_TRY(cudaMemcpyAsync(ns, d_out_start_, out_cap_ * 4, cudaMemcpyDeviceToDevice, s));
+        PSS_CUDA_TRY(cudaMemcpyAsync(ne, d_out_end_, out_cap_ * 4, cudaMemcpyDeviceToDevice, s));
+        PSS_CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    cudaFree(d_out_chunk_); cudaFree(d_out_start_); cudaFree(d_out_end_);
+    d_out_chunk_ = nc; d_out_start_ = ns; d_out_end_ = ne;
+    out_cap_ = cap;
+    return PSS_OK;
+}
+
+int Searcher::search_small(const uint8_t *h_patterns, const int64_t *h_offsets, int32_t nq, SearchOutput *out,
+                           SearchTimes *times, bool *handled) {
+    *handled = false;
     if (device_ < 0) return fail(PSS_ERR_ARG, "searcher not initialised");
-    if (nq < 0 || !sink) return fail(PSS_ERR_ARG, "bad search arguments");
-    if (n_hits) *n_hits = 0;
+    const int nc = (int)chunks_.size();
+    const int64_t npairs = (int64_t)nq * nc;
+    if (!small_path_ || nq <= 0 || nq > SMALL_MAX_QUERIES || npairs <= 0 || npairs > SMALL_MAX_PAIRS) return PSS_OK;
+    if (h_offsets[nq] > SMALL_PAT_BYTES) return PSS_OK;
+    SmallPatterns pats;
+    pats.nq = (uint32_t)nq;
+    for (int32_t q = 0; q <= nq; ++q) pats.off[q] = (uint32_t)h_offsets[q];
+    if (h_offsets[nq]) std::memcpy(pats.bytes, h_patterns, (size_t)h_offsets[nq]);
+    PSS_CUDA_TRY(cudaSetDevice(device_));
+    const uint32_t seq = ++small_seq_ ? small_seq_ : ++small_seq_;   // never 0
+    unsigned char *d_out = nullptr;
+    PSS_CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_out), h_small_out_, 0));
+    const auto t0 = std::chrono::steady_clock::now();
+    small_search_kernel<<<(unsigned)npairs, SMALL_THREADS, sizeof(SmallSmem), stream_>>>(
+        d_chunks_, nc, pats, (uint32_t)npairs, seq, d_lb_, d_cnt_, d_scalar_ + 3, d_out);
+    PSS_LAUNCH_CHECK();
+    // The kernel writes its result into mapped pinned memory and the sequence number last:
+    // poll it instead of paying a stream synchronisation.  cudaStreamQuery now and then
+    // catches a failed launch (which would never write the word).
+    volatile SmallHeader *hdr = reinterpret_cast<volatile SmallHeader *>(h_small_out_);
+    uint32_t spins = 0;
+    while (hdr->seq != seq) {
+        if ((++spins & 0xFFFu) == 0) {
+            cudaError_t q = cudaStreamQuery(stream_);
+            if (q != cudaErrorNotReady) {
+                if (q != cudaSuccess) return fail(PSS_ERR_CUDA, std::string("small search kernel: ") + cudaGetErrorString(q));
+                if (hdr->seq != seq) PSS_CUDA_TRY(cudaStreamSynchronize(stream_));
+                if (hdr->seq != seq) return fail(PSS_ERR_CUDA, "small search kernel finished without publishing a result");
+            }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (times) {
+        *times = SearchTimes();
+        times->ms_bounds = times->ms_total =
+            std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    if (hdr->status != 0) return PSS_OK;    // too many matching suffixes: not handled (lb/cnt are recomputed)
+    const SmallHeader *h = reinterpret_cast<const SmallHeader *>(h_small_out_);
+    out->on_host     = true;
+    out->n_entries   = h->n_entries;
+    out->n_hits      = h->n_hits;
+    out->d_entry_off = h->entry_off;
+    out->d_query_off = reinterpret_cast<const int64_t *>(h->query_off);
+    out->d_chunk     = reinterpret_cast<const int32_t *>(h_small_out_ + sizeof(SmallHeader));
+    out->d_start     = reinterpret_cast<const uint32_t *>(out->d_chunk + SMALL_CAP);
+    out->d_end       = out->d_start + SMALL_CAP;
+    *handled = true;
+    return PSS_OK;
+}
+
+int Searcher::search(const uint8_t *d_patterns, const int64_t *d_offsets, int32_t nq, cudaStream_t stream,
+                     SearchOutput *out, SearchTimes *times) {
+    if (device_ < 0) return fail(PSS_ERR_ARG, "searcher not initialised");
+    if (nq < 0 || !out) return fail(PSS_ERR_ARG, "bad search arguments");
+    *out = SearchOutput();
     if (times) *times = SearchTimes();
     const int nc = (int)chunks_.size();
     const int64_t npairs64 = (int64_t)nq * nc;
-    if (npairs64 == 0) return PSS_OK;
-    if (npairs64 >= (1ll << 31)) return fail(PSS_ERR_ARG, "too many (query, chunk) pairs in one batch");
+    if (npairs64 >= (1ll << 31) - 1) return fail(PSS_ERR_ARG, "too many (query, chunk) pairs in one batch");
     PSS_CUDA_TRY(cudaSetDevice(device_));
     cudaStream_t s = stream ? stream : stream_;
     const uint32_t npairs = (uint32_t)npairs64;
-    PSS_TRY(ensure_pairs(npairs));
+    PSS_TRY(ensure_pairs(std::max<int64_t>(npairs, 1), std::max<int64_t>(nq, 1)));
+    out->d_entry_off = d_entry_off_;
+    out->d_query_off = d_query_off_;
+    if (npairs == 0) {
+        PSS_CUDA_TRY(cudaMemsetAsync(d_entry_off_, 0, sizeof(uint32_t), s));
+        PSS_CUDA_TRY(cudaMemsetAsync(d_query_off_, 0, ((size_t)nq + 1) * sizeof(int64_t), s));
+        PSS_CUDA_TRY(cudaStreamSynchronize(s));
+        return PSS_OK;
+    }
 
     uint32_t max_n = 1;
     for (const auto &c : chunks_) max_n = std::max(max_n, c.n);
     const int sbits = std::max(1, bit_width_u64((uint64_t)max_n - 1));
 
-    // ---- small batches: one fused kernel, one device→host copy -------------------------------
-    bool have_bounds = false;
-    if (small_path_ && npairs <= (uint32_t)SMALL_MAX_PAIRS) {
-        PSS_CUDA_TRY(cudaEventRecord(ev_[0], s));
-        small_search_kernel<<<1, SMALL_THREADS, sizeof(SmallSmem), s>>>(d_chunks_, nc, d_patterns, d_offsets, npairs, d_lb_,
-                                                                       d_cnt_, d_small_out_);
-        PSS_LAUNCH_CHECK();
-        PSS_CUDA_TRY(cudaEventRecord(ev_[1], s));
-        PSS_CUDA_TRY(cudaMemcpyAsync(h_small_out_, d_small_out_, SMALL_OUT_BYTES, cudaMemcpyDeviceToHost, s));
-        PSS_CUDA_TRY(cudaStreamSynchronize(s));
-        const SmallHeader *hdr = reinterpret_cast<const SmallHeader *>(h_small_out_);
-        if (hdr->status == 0) {
-            const int32_t *hq  = reinterpret_cast<const int32_t *>(h_small_out_ + sizeof(SmallHeader));
-            const int32_t *hc  = hq + SMALL_CAP;
-            const uint32_t *hs = reinterpret_cast<const uint32_t *>(hc + SMALL_CAP);
-            const uint32_t *he = hs + SMALL_CAP;
-            if (n_hits) *n_hits = hdr->n_hits;
-            if (per_pair_count)
-                for (uint32_t p = 0; p < npairs; ++p) per_pair_count[p] = hdr->pair_entries[p];
-            if (times) {
-                float ms = 0.f;
-                PSS_CUDA_TRY(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
-                times->ms_bounds = ms;   // the fused kernel: bounds + extract + dedup
-            }
-            return sink->deliver_host(hdr->n_entries, hq, hc, hs, he, s);
-        }
-        have_bounds = true;   // too many hits: lb/cnt are already in d_lb_/d_cnt_
-    }
-
-    // ---- bounds -----------------------------------------------------------------------
+    // ---- bounds + hit offsets, one host read: the number of matching suffixes ----------------
     PSS_CUDA_TRY(cudaEventRecord(ev_[0], s));
-    if (!have_bounds) {
     bounds_kernel<<<(unsigned)div_up((int64_t)npairs * 32, BD_THREADS), BD_THREADS, 0, s>>>(
         d_chunks_, nc, d_patterns, d_offsets, npairs, d_lb_, d_cnt_);
     PSS_LAUNCH_CHECK();
-    }
     PSS_CUDA_TRY(cudaEventRecord(ev_[1], s));
-    PSS_CUDA_TRY(cudaMemcpyAsync(h_cnt_, d_cnt_, npairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    hit_offsets_kernel<<<1, SCAN_THREADS, 0, s>>>(d_cnt_, npairs, d_hit_off_,
+                                                   reinterpret_cast<unsigned long long *>(d_scalar_));
+    PSS_LAUNCH_CHECK();
+    PSS_CUDA_TRY(cudaMemcpyAsync(h_scalar_, d_scalar_, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     PSS_CUDA_TRY(cudaStreamSynchronize(s));
-    {
-        float ms = 0.f;
-        PSS_CUDA_TRY(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
-        if (times) times->ms_bounds += ms;
-    }
-    if (per_pair_count) std::memset(per_pair_count, 0, sizeof(int64_t) * npairs);
+    const uint64_t total_hits = (uint64_t)h_scalar_[0] | ((uint64_t)h_scalar_[1] << 32);
+    out->n_hits = (int64_t)total_hits;
 
-    // ---- sub-batches of pairs whose hits fit the workspace ----------------------------------
+    // ---- sub-batches of pairs whose hits fit the workspace (normally: one) --------------------
     constexpr int64_t HIT_BUDGET = 1ll << 27;
-    uint32_t a = 0;
-    while (a < npairs) {
-        int64_t H = 0;
-        uint32_t b = a;
-        while (b < npairs && (H == 0 || H + h_cnt_[b] <= HIT_BUDGET)) {
-            H += h_cnt_[b];
-            ++b;
+    struct Sub { uint32_t a, np; uint32_t nh; uint32_t hit_base; bool device_offsets; };
+    std::vector<Sub> subs;
+    if (total_hits <= (uint64_t)HIT_BUDGET) {
+        if (total_hits) subs.push_back({0u, npairs, (uint32_t)total_hits, 0u, true});
+    } else {
+        // oversized batch: the per-pair counts come to the host once and are cut there
+        if (!h_cnt_) {
+            PSS_CUDA_TRY(cudaMallocHost(&h_cnt_, (size_t)pair_cap_ * sizeof(uint32_t)));
+            PSS_CUDA_TRY(cudaMallocHost(&h_hit_off_, ((size_t)pair_cap_ + 1) * sizeof(uint32_t)));
         }
-        if (H >= (1ll << 30)) return fail(PSS_ERR_ARG, "a single (query, chunk) pair has >= 2^30 hits");
-        const uint32_t np = b - a;
-        if (H == 0) { a = b; continue; }
-        if (n_hits) *n_hits += H;
-        uint32_t run = 0;
-        for (uint32_t p = 0; p < np; ++p) {
-            h_hit_off_[p] = run;
-            run += h_cnt_[a + p];
+        PSS_CUDA_TRY(cudaMemcpyAsync(h_cnt_, d_cnt_, (size_t)npairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        PSS_CUDA_TRY(cudaStreamSynchronize(s));
+        uint32_t a = 0;
+        while (a < npairs) {
+            int64_t H = 0;
+            uint32_t b = a;
+            while (b < npairs && (H == 0 || H + h_cnt_[b] <= HIT_BUDGET)) H += h_cnt_[b++];
+            if (H >= (1ll << 30)) return fail(PSS_ERR_ARG, "a single (query, chunk) pair has >= 2^30 hits");
+            if (H) subs.push_back({a, b - a, (uint32_t)H, 0u, false});
+            a = b;
         }
-        h_hit_off_[np] = run;
-        const uint32_t nh = (uint32_t)H;
-        PSS_TRY(ensure_hits(H));
-        PSS_CUDA_TRY(cudaMemcpyAsync(d_hit_off_, h_hit_off_, (np + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    }
 
+    uint32_t entries = 0;          // entries produced so far (all sub-batches)
+    uint32_t next_pair = 0;        // entry_off is filled up to here
+    float ms_extract = 0.f, ms_dedup = 0.f;
+    for (const Sub &sb : subs) {
+        PSS_TRY(ensure_hits(sb.nh));
+        if ((int64_t)entries + sb.nh >= (1ll << 32)) return fail(PSS_ERR_ARG, "more than 2^32 entries in one batch");
+        PSS_TRY(ensure_out((int64_t)entries + sb.nh, s));   // entries <= matching suffixes: no count needed up front
+        const uint32_t *hit_off = d_hit_off_ + sb.a;
+        uint32_t hit_base = 0;
+        if (sb.device_offsets) {
+            hit_base = 0;                                    // a == 0: offsets are already relative
+        } else {
+            uint32_t run = 0;
+            for (uint32_t p = 0; p < sb.np; ++p) { h_hit_off_[p] = run; run += h_cnt_[sb.a + p]; }
+            h_hit_off_[sb.np] = run;
+            PSS_CUDA_TRY(cudaMemcpyAsync(d_hit_off_ + sb.a, h_hit_off_, ((size_t)sb.np + 1) * sizeof(uint32_t),
+                                         cudaMemcpyHostToDevice, s));
+        }
+        // pairs skipped between sub-batches (no hits) get their entry offset here
+        if (sb.a > next_pair) {
+            std::vector<uint32_t> fill(sb.a - next_pair, entries);
+            PSS_CUDA_TRY(cudaMemcpyAsync(d_entry_off_ + next_pair, fill.data(), fill.size() * sizeof(uint32_t),
+                                         cudaMemcpyHostToDevice, s));
+            PSS_CUDA_TRY(cudaStreamSynchronize(s));
+        }
+        const uint32_t nh = sb.nh;
         PSS_CUDA_TRY(cudaEventRecord(ev_[2], s));
-        extract_kernel<<<(unsigned)div_up(nh, 256), 256, 0, s>>>(d_chunks_, nc, a, np, d_hit_off_, d_lb_, nh, sbits,
-                                                                d_keys_, d_end_);
+        extract_kernel<<<(unsigned)div_up(nh, 256), 256, 0, s>>>(d_chunks_, nc, sb.a, sb.np, hit_off, hit_base, d_lb_, nh,
+                                                                sbits, d_keys_, d_end_);
         PSS_LAUNCH_CHECK();
         PSS_CUDA_TRY(cudaEventRecord(ev_[3], s));
 
         bool in_alt = false;
-        const int end_bit = sbits + std::max(1, bit_width_u64((uint64_t)np - 1));
-        PSS_TRY(sorter_.sort(d_keys_, d_keys_alt_, d_vals_, d_vals_alt_, nh, 0, end_bit, /*iota=*/true, s, &in_alt, nullptr));
+        const int end_bit = sbits + std::max(1, bit_width_u64((uint64_t)sb.np - 1));
+        PSS_TRY(sorter_.sort_async(d_keys_, d_keys_alt_, d_vals_, d_vals_alt_, nh, 0, end_bit, /*iota=*/true, s, &in_alt));
         const uint64_t *k_sorted = in_alt ? d_keys_alt_ : d_keys_;
         const uint32_t *v_sorted = in_alt ? d_vals_alt_ : d_vals_;
         const uint32_t tiles = (uint32_t)div_up(nh, CP_TILE);
@@ -659,44 +1007,53 @@ int Searcher::search(const uint8_t *d_patterns, const int64_t *d_offsets, int32_
         PSS_LAUNCH_CHECK();
         flag_reduce_kernel<<<tiles, CP_THREADS, 0, s>>>(d_flag_, nh, d_tile_sum_);
         PSS_LAUNCH_CHECK();
-        tile_scan_kernel<<<1, 1024, 0, s>>>(d_tile_sum_, tiles, d_scalar_);
+        tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(d_tile_sum_, tiles, d_scalar_ + 2);
         PSS_LAUNCH_CHECK();
-        PSS_CUDA_TRY(cudaMemcpyAsync(h_scalar_, d_scalar_, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        PSS_CUDA_TRY(cudaStreamSynchronize(s));
-        const int64_t kept = h_scalar_[0];
-
-        int32_t *o_q = nullptr, *o_c = nullptr;
-        uint32_t *o_s = nullptr, *o_e = nullptr;
-        PSS_TRY(sink->reserve(kept, &o_q, &o_c, &o_s, &o_e));
-        if (!o_s || !o_e) return fail(PSS_ERR_ARG, "search sink returned null output buffers");
-        if (per_pair_count)   // pairs without hits never get an entry: keep the copied-back array defined
-            PSS_CUDA_TRY(cudaMemsetAsync(d_pair_first_, 0, (size_t)np * sizeof(uint32_t), s));
-        compact_kernel<<<tiles, CP_THREADS, 0, s>>>(d_flag_, d_end_, d_tile_sum_, d_hit_off_, d_chunks_, nc, a, np, nh,
-                                                    d_pair_first_, o_q, o_c, o_s, o_e);
+        PSS_CUDA_TRY(cudaMemsetAsync(d_pair_first_, 0xFF, (size_t)sb.np * sizeof(uint32_t), s));
+        compact_kernel<<<tiles, CP_THREADS, 0, s>>>(d_flag_, d_end_, d_tile_sum_, hit_off, hit_base, d_chunks_, nc, sb.a,
+                                                    sb.np, nh, d_pair_first_, d_out_chunk_ + entries,
+                                                    d_out_start_ + entries, d_out_end_ + entries);
+        PSS_LAUNCH_CHECK();
+        entry_offsets_kernel<<<1, SCAN_THREADS, 0, s>>>(d_pair_first_, sb.np, d_scalar_ + 2, entries, d_entry_off_ + sb.a);
         PSS_LAUNCH_CHECK();
         PSS_CUDA_TRY(cudaEventRecord(ev_[4], s));
-        PSS_TRY(sink->commit(kept, s));
-        if (per_pair_count) {
-            PSS_CUDA_TRY(cudaMemcpyAsync(h_pair_first_, d_pair_first_, np * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-            PSS_CUDA_TRY(cudaStreamSynchronize(s));
-            // pairs without hits have no pair_first entry: walk backwards from the total
-            int64_t next = kept;
-            for (int64_t p = (int64_t)np - 1; p >= 0; --p) {
-                if (h_cnt_[a + p] == 0) continue;
-                per_pair_count[a + p] = next - (int64_t)h_pair_first_[p];
-                next = h_pair_first_[p];
-            }
-        } else {
-            PSS_CUDA_TRY(cudaStreamSynchronize(s));
-        }
+        PSS_CUDA_TRY(cudaMemcpyAsync(h_scalar_ + 2, d_scalar_ + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        PSS_CUDA_TRY(cudaMemcpyAsync(h_scalar_ + 8, sorter_.d_error_flag(), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        PSS_CUDA_TRY(cudaStreamSynchronize(s));
+        if (h_scalar_[8]) return sorter_.poll_error(s);
+        entries += h_scalar_[2];
+        next_pair = sb.a + sb.np;
         if (times) {
             float ms = 0.f;
             PSS_CUDA_TRY(cudaEventElapsedTime(&ms, ev_[2], ev_[3]));
-            times->ms_extract += ms;
+            ms_extract += ms;
             PSS_CUDA_TRY(cudaEventElapsedTime(&ms, ev_[3], ev_[4]));
-            times->ms_dedup += ms;
+            ms_dedup += ms;
         }
-        a = b;
+    }
+    // pairs after the last sub-batch with hits (or all pairs when nothing matched)
+    if (next_pair <= npairs) {
+        std::vector<uint32_t> fill((size_t)npairs - next_pair + 1, entries);
+        if (next_pair == 0 || next_pair < npairs) {
+            // entry_offsets_kernel already wrote entry_off[next_pair] = entries when a sub-batch ran
+            PSS_CUDA_TRY(cudaMemcpyAsync(d_entry_off_ + next_pair, fill.data(), fill.size() * sizeof(uint32_t),
+                                         cudaMemcpyHostToDevice, s));
+            PSS_CUDA_TRY(cudaStreamSynchronize(s));   // `fill` is pageable: complete before it goes out of scope
+        }
+    }
+    query_offsets_kernel<<<(unsigned)div_up((int64_t)nq + 1, 256), 256, 0, s>>>(d_entry_off_, (uint32_t)nq, (uint32_t)nc,
+                                                                               d_query_off_);
+    PSS_LAUNCH_CHECK();
+    out->n_entries = entries;
+    out->d_chunk   = d_out_chunk_;
+    out->d_start   = d_out_start_;
+    out->d_end     = d_out_end_;
+    if (times) {
+        float ms = 0.f;
+        PSS_CUDA_TRY(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
+        times->ms_bounds  = ms;
+        times->ms_extract = ms_extract;
+        times->ms_dedup   = ms_dedup;
     }
     return PSS_OK;
 }

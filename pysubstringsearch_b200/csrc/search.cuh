@@ -8,10 +8,19 @@
 //            pattern bytes in registers, text compared in coalesced 32-byte windows
 //            (lib.rs:212-252 computes the same range with two sequential binary searches)
 //   extract  one thread per matching suffix: entry start = 1 + previous '\n', entry end =
-//            next '\n' (lib.rs:266-273), found with 4-byte SIMD compares
+//            next '\n' (lib.rs:266-273): a short SIMD scan around the hit, and beyond
+//            SCAN_LIMIT bytes one binary search in the chunk's newline side index
+//            (sorted '\n' offsets, derived on the device when the chunk is loaded), so the
+//            cost per hit is bounded whatever the line length
 //   dedup    stable onesweep sort of (pair id, entry start) → the first record of every
 //            run is the entry's first hit in SA order (lib.rs:262,274 uses a hash set);
 //            survivors are compacted back in SA order, which is the reference's order
+//
+// Counts, offsets and the per-(query, chunk) entry offsets stay on the device; the host
+// reads two scalars per batch (matching suffixes, entries).  A batch of a few pairs
+// (a single Reader.search) is answered by ONE launch: every pair's bounds by a CTA-wide
+// 512-ary search (4 dependent probes instead of 58), the last CTA to finish extracts,
+// dedups and writes the tuples straight into mapped pinned host memory.
 #pragma once
 
 #include <vector>
@@ -22,30 +31,40 @@
 namespace pss {
 
 struct DeviceChunk {
-    const uint8_t *text;   // device, zero-padded to a multiple of 16 bytes past n
-    const int32_t *sa;     // device
-    uint32_t       n;
-    int32_t        global_id;
+    const uint8_t  *text;      // device, 16 readable zero bytes past n
+    const int32_t  *sa;        // device
+    const uint32_t *nl;        // device: sorted offsets of every '\n' (may be null: unbounded scans)
+    uint32_t        n;
+    uint32_t        n_lines;   // entries of nl
+    int32_t         global_id;
+    int32_t         reserved;
 };
 
 struct SearchTimes {
     float ms_bounds = 0.f, ms_extract = 0.f, ms_dedup = 0.f, ms_total = 0.f;
 };
 
-// Receives the entries of one sub-batch, already in final order, while they are still
-// on the device.
-struct SearchSink {
-    virtual ~SearchSink() {}
-    // Called before the compaction kernel of a sub-batch: `count` entries are about to be
-    // produced; return the device pointers they must be written to (any may be nullptr).
-    virtual int reserve(int64_t count, int32_t **d_query, int32_t **d_chunk, uint32_t **d_start,
-                        uint32_t **d_end) = 0;
-    // Called after the compaction kernel has been enqueued on `stream`.
-    virtual int commit(int64_t count, cudaStream_t stream) = 0;
-    // Small-batch path: the entries are already in (pinned) host memory.  The default
-    // forwards them through reserve()/commit(); host sinks override it with a plain copy.
-    virtual int deliver_host(int64_t count, const int32_t *query, const int32_t *chunk, const uint32_t *start,
-                             const uint32_t *end, cudaStream_t stream);
+// Result of one batch, resident on the searcher's device and owned by the searcher
+// (valid until its next search).  Entries are in (query, local chunk, SA order of first
+// hit) order; pair p = query * num_chunks + local chunk.
+struct SearchOutput {
+    int64_t         n_entries = 0, n_hits = 0;
+    const uint32_t *d_entry_off = nullptr;   // [npairs + 1] entries before pair p
+    const int32_t  *d_chunk = nullptr;       // [n_entries] global chunk id
+    const uint32_t *d_start = nullptr;       // [n_entries] entry start (line_tail, lib.rs:270-273)
+    const uint32_t *d_end = nullptr;         // [n_entries] offset of the terminating '\n' (line_head, lib.rs:266-269)
+    const int64_t  *d_query_off = nullptr;   // [nq + 1] entries before query q
+    bool            on_host = false;         // small path: the five arrays are (mapped pinned) HOST pointers
+};
+
+// Patterns of a small batch, passed to the fused kernel by value (no H2D copy).
+constexpr int SMALL_MAX_PAIRS   = 64;
+constexpr int SMALL_MAX_QUERIES = 64;
+constexpr int SMALL_PAT_BYTES   = 1024;
+struct SmallPatterns {
+    uint32_t nq;
+    uint32_t off[SMALL_MAX_QUERIES + 1];
+    uint8_t  bytes[SMALL_PAT_BYTES];
 };
 
 class Searcher {
@@ -59,18 +78,29 @@ public:
     void release();
     int  set_chunks(const std::vector<DeviceChunk> &chunks);
     int  num_chunks() const { return (int)chunks_.size(); }
+    const std::vector<DeviceChunk> &chunks() const { return chunks_; }
     cudaStream_t stream() const { return stream_; }
     int  device() const { return device_; }
 
-    // d_patterns / d_offsets: device.  Entries are delivered to `sink` sub-batch by
-    // sub-batch in (query, chunk, SA order) order.  per_pair_count (host, nq * num_chunks,
-    // may be nullptr) receives the entries produced by each (query, chunk) pair.
+    // Builds the newline side index of a chunk already resident on this device: *d_nl
+    // (cudaMalloc'ed here, owned by the caller) and *n_lines.
+    int build_newline_index(const uint8_t *d_text, uint32_t n, uint32_t **d_nl, uint32_t *n_lines);
+
+    // d_patterns / d_offsets: device.  Synchronises `stream` before returning (the counts
+    // in *out are host values).
     int search(const uint8_t *d_patterns, const int64_t *d_offsets, int32_t nq, cudaStream_t stream,
-               SearchSink *sink, int64_t *per_pair_count, int64_t *n_hits, SearchTimes *times);
+               SearchOutput *out, SearchTimes *times);
+
+    // Single-launch path for host-side callers: patterns (host) are passed by value.
+    // *handled = false when the batch does not qualify (too many pairs / pattern bytes /
+    // matching suffixes); nothing has been produced then and search() must be used.
+    int search_small(const uint8_t *h_patterns, const int64_t *h_offsets, int32_t nq, SearchOutput *out,
+                     SearchTimes *times, bool *handled);
 
 private:
-    int ensure_pairs(int64_t npairs);
+    int ensure_pairs(int64_t npairs, int64_t nq);
     int ensure_hits(int64_t nhits);
+    int ensure_out(int64_t entries, cudaStream_t s);
 
     int          device_ = -1;
     cudaStream_t stream_ = nullptr;
@@ -78,16 +108,26 @@ private:
     std::vector<DeviceChunk> chunks_;
     DeviceChunk *d_chunks_ = nullptr;
 
-    int64_t   pair_cap_ = 0;
+    int64_t   pair_cap_ = 0, query_cap_ = 0;
     uint32_t *d_lb_ = nullptr, *d_cnt_ = nullptr, *d_hit_off_ = nullptr, *d_pair_first_ = nullptr;
-    uint32_t *h_lb_ = nullptr, *h_cnt_ = nullptr, *h_hit_off_ = nullptr, *h_pair_first_ = nullptr;  // pinned
+    uint32_t *d_entry_off_ = nullptr;
+    int64_t  *d_query_off_ = nullptr;
+    uint32_t *h_cnt_ = nullptr, *h_hit_off_ = nullptr;   // pinned; only the oversized-batch path uses them
 
     int64_t   hit_cap_ = 0;
     uint64_t *d_keys_ = nullptr, *d_keys_alt_ = nullptr;
     uint32_t *d_vals_ = nullptr, *d_vals_alt_ = nullptr;
     uint32_t *d_end_ = nullptr, *d_flag_ = nullptr, *d_tile_sum_ = nullptr;
+
+    int64_t   out_cap_ = 0;
+    int32_t  *d_out_chunk_ = nullptr;
+    uint32_t *d_out_start_ = nullptr, *d_out_end_ = nullptr;
+
+    // scalars: [0..1] total matching suffixes (u64), [2] entries of the current sub-batch,
+    // [3] small-path ticket
     uint32_t *d_scalar_ = nullptr, *h_scalar_ = nullptr;
-    unsigned char *d_small_out_ = nullptr, *h_small_out_ = nullptr;   // small-batch path result block
+    unsigned char *h_small_out_ = nullptr;   // mapped pinned result block of the small path
+    uint32_t  small_seq_ = 0;
     bool      small_path_ = true;
     cudaEvent_t ev_[8] = {};
 };
