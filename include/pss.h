@@ -365,6 +365,10 @@ int32_t pss_reader_search_batch_dist_device(pss_reader *r, pss_comm *c, const ui
 
 void pss_result_free(pss_result *res);
 
+/* Copies `bytes` from device memory (e.g. a pss_device_result array) to host memory, for
+ * callers that do not link a CUDA runtime themselves.  Synchronous. */
+int32_t pss_memcpy_d2h(void *dst, const void *d_src, size_t bytes);
+
 /* Number of kernels this library has launched in the calling process (for bench.py's
  * gpu_launches claim). */
 int64_t pss_kernel_launch_count(void);

@@ -40,6 +40,7 @@ lib.pss_reader_search_batch_device.argtypes = [vp, vp, vp, i32, i64, vp, vp]
 lib.pss_sa_build_begin.argtypes = [i32, vp, i32, C.POINTER(vp)]
 lib.pss_sa_build_wait.argtypes = [vp, vp]
 lib.pss_release_cached.argtypes = []
+lib.pss_memcpy_d2h.argtypes = [vp, vp, sz]
 lib.pss_writer_open_devices.argtypes = [C.c_char_p, i64, vp, i32, C.POINTER(vp)]
 lib.pss_writer_would_flush.argtypes = [vp, sz]
 lib.pss_reader_open_devices.argtypes = [C.c_char_p, vp, i32, C.POINTER(vp)]
@@ -99,6 +100,14 @@ def libsais(text):
     sa = np.empty(len(t), dtype=np.int32)
     check(lib.pss_libsais(t.ctypes.data, sa.ctypes.data, len(t), 0, None))
     return sa
+
+
+def from_device(ptr, n, dtype):
+    """n elements of `dtype` at device pointer `ptr` → numpy array"""
+    out = np.empty(n, dtype=dtype)
+    if n:
+        check(lib.pss_memcpy_d2h(out.ctypes.data, ptr, out.nbytes))
+    return out
 
 
 def result_arrays(res):

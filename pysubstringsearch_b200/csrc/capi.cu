@@ -114,6 +114,12 @@ int32_t pss_sa_build_wait(pss_sa_build *h, int32_t *SA) {
     return job->engine->wait(job, SA);
 }
 
+int32_t pss_memcpy_d2h(void *dst, const void *d_src, size_t bytes) {
+    if (bytes && (!dst || !d_src)) return fail(PSS_ERR_ARG, "null pointer");
+    if (bytes) PSS_CUDA_TRY(cudaMemcpy(dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    return PSS_OK;
+}
+
 int32_t pss_release_cached(void) {
     BuildEngine::release_idle();
     return PSS_OK;

@@ -374,6 +374,7 @@ int RadixSorter::init(int device) {
     PSS_CUDA_TRY(cudaMalloc(&d_hist_, MAX_PASSES * RADIX * sizeof(uint32_t)));
     PSS_CUDA_TRY(cudaMalloc(&d_bin_base_, MAX_PASSES * RADIX * sizeof(uint32_t)));
     PSS_CUDA_TRY(cudaMalloc(&d_ctrl_, CTRL_WORDS * sizeof(uint32_t)));
+    PSS_CUDA_TRY(cudaMemset(d_ctrl_, 0, CTRL_WORDS * sizeof(uint32_t)));   // the error flag is sticky across sort_async calls
     PSS_CUDA_TRY(cudaMallocHost(&h_ctrl_, CTRL_WORDS * sizeof(uint32_t)));
     for (auto &e : ev_) PSS_CUDA_TRY(cudaEventCreate(&e));
     ev_ready_ = true;

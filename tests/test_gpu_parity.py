@@ -363,6 +363,13 @@ def test_multi_device_reader_front(pss, oracle, monkeypatch):
         o.close()
 
 
+def _device_result_arrays(pss, dr):
+    return (pss.from_device(dr.d_query_offsets, dr.n_queries + 1, np.int64),
+            pss.from_device(dr.d_chunk_id, dr.n_entries, np.int32),
+            pss.from_device(dr.d_line_start, dr.n_entries, np.uint32),
+            pss.from_device(dr.d_line_end, dr.n_entries, np.uint32))
+
+
 def test_device_resident_search_matches_host_api(pss):
     import torch
     text = synth.zipf_words_text(1_000_000, seed=51, vocab=2048, block=1 << 16)
@@ -376,27 +383,185 @@ def test_device_resident_search_matches_host_api(pss):
         blob, offs = synth.pack_patterns(pats)
         d_blob = torch.from_numpy(blob).cuda()
         d_offs = torch.from_numpy(offs).cuda()
-        cap = len(ch) + 10
-        out = [torch.empty(cap, dtype=torch.int32, device="cuda") for _ in range(4)]
-        n_entries, n_hits = C.c_int64(0), C.c_int64(0)
         torch.cuda.synchronize()
+        dr = pss.DeviceResult()
         rc = pss.lib.pss_reader_search_batch_device(r.h, d_blob.data_ptr(), d_offs.data_ptr(), len(pats), int(offs[-1]),
-                                                    out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
-                                                    out[3].data_ptr(), cap, C.byref(n_entries), C.byref(n_hits), None)
+                                                    C.byref(dr), None)
         assert rc == 0, pss.err()
-        k = n_entries.value
-        assert k == len(ch)
-        q = np.repeat(np.arange(len(pats)), np.diff(qo))
-        assert np.array_equal(out[0][:k].cpu().numpy(), q)
-        assert np.array_equal(out[1][:k].cpu().numpy(), ch)
-        assert np.array_equal(out[2][:k].cpu().numpy().view(np.uint32), st)
-        assert np.array_equal(out[3][:k].cpu().numpy().view(np.uint32), en)
-        # too-small buffers: reports the size needed, returns PSS_ERR_NOMEM
-        rc = pss.lib.pss_reader_search_batch_device(r.h, d_blob.data_ptr(), d_offs.data_ptr(), len(pats), int(offs[-1]),
-                                                    out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
-                                                    out[3].data_ptr(), 3, C.byref(n_entries), C.byref(n_hits), None)
-        assert rc == -2 and n_entries.value == len(ch)
+        assert dr.n_entries == len(ch) and dr.n_queries == len(pats) and dr.n_chunks == r.num_chunks
+        gqo, gch, gst, gen = _device_result_arrays(pss, dr)
+        assert np.array_equal(gqo, qo) and np.array_equal(gch, ch) and np.array_equal(gst, st) and np.array_equal(gen, en)
+        # per-(query, chunk) entry offsets: the exclusive scan of the per-pair entry counts
+        npairs = len(pats) * r.num_chunks
+        eo = pss.from_device(dr.d_entry_offsets, npairs + 1, np.uint32).astype(np.int64)
+        pair = np.repeat(np.arange(len(pats)), np.diff(qo)) * r.num_chunks + ch
+        want = np.concatenate(([0], np.cumsum(np.bincount(pair, minlength=npairs))))
+        assert np.array_equal(eo, want)
         r.close()
+
+
+def test_bad_pattern_offsets_are_rejected(pss):
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "o.idx")
+        _write(pss.Writer, p, [b"alpha", b"beta"], None)
+        r = pss.Reader(p)
+        blob = np.frombuffer(b"alphabeta", dtype=np.uint8).copy()
+        res = C.c_void_p()
+        for bad in ([1, 5, 9], [0, 6, 5], [0, -1, 4]):
+            offs = np.array(bad, dtype=np.int64)
+            assert pss.lib.pss_reader_search_batch(r.h, blob.ctypes.data, offs.ctypes.data, 2, C.byref(res)) == -1
+        r.close()
+
+
+def test_async_build_seam_pipelined(pss, oracle):
+    """pss_sa_build_begin/_wait: several builds queued at once (two device slots), pageable and
+    pinned destinations, every suffix array identical to the oracle's."""
+    import torch
+    texts = [synth.zipf_words_text(n, seed=100 + i, vocab=4096, block=1 << 16)
+             for i, n in enumerate([3_000_000, 1, 10_000_000, 70_000, 9_000_000, 2])]
+    handles = []
+    for t in texts[:2]:
+        h = C.c_void_p()
+        pss.check(pss.lib.pss_sa_build_begin(-1, t.ctypes.data, len(t), C.byref(h)))
+        handles.append(h)
+    out = []
+    for k, t in enumerate(texts):
+        if k + 2 < len(texts):                      # keep two builds in flight ahead of the one waited for
+            h = C.c_void_p()
+            pss.check(pss.lib.pss_sa_build_begin(-1, texts[k + 2].ctypes.data, len(texts[k + 2]), C.byref(h)))
+            handles.append(h)
+        if k % 2 == 0:
+            sa = np.empty(len(t), dtype=np.int32)
+            pss.check(pss.lib.pss_sa_build_wait(handles[k], sa.ctypes.data))
+        else:
+            pinned = torch.empty(len(t), dtype=torch.int32).pin_memory()
+            pss.check(pss.lib.pss_sa_build_wait(handles[k], pinned.data_ptr()))
+            sa = pinned.numpy().copy()
+        out.append(sa)
+    for t, sa in zip(texts, out):
+        assert np.array_equal(sa, oracle.suffix_array_port(t))
+    assert pss.lib.pss_sa_build_wait(None, None) == -1
+    assert pss.lib.pss_release_cached() == 0
+    assert np.array_equal(pss.libsais(texts[3]), out[3])          # the workspace regrows after a release
+
+
+def test_writer_explicit_device_list(pss, oracle):
+    """Chunk k → devices[k % G]: builds run on per-device engines, records reach the file in chunk order."""
+    text = synth.zipf_words_text(6_000_000, seed=23, vocab=4096, block=1 << 16)
+    entries = bytes(text).split(b"\n")[:-1]
+    ndev = pss.lib.pss_device_count()
+    lists = [[0], [0, 0, 0]] + ([list(range(ndev))] if ndev >= 2 else [])
+    with tempfile.TemporaryDirectory() as d:
+        b = os.path.join(d, "cpu.idx")
+        _write(oracle.Writer, b, entries, 1 << 20)
+        want = open(b, "rb").read()
+        for devs in lists:
+            a = os.path.join(d, "gpu.idx")
+            w = pss.Writer(a, 1 << 20, devices=devs)
+            for e in entries:
+                assert w.add_entry(e) == 0
+            assert w.finalize() == 0
+            w.close()
+            assert open(a, "rb").read() == want, devs
+            r = pss.Reader(a, devices=devs)
+            o = oracle.Reader(b)
+            _compare_searches(r, o, [b"e ", b"", bytes(text[500:520])])
+            r.close()
+            o.close()
+
+
+def test_newline_side_index_long_lines(pss, oracle):
+    """Entries far longer than the scan window: extraction goes through the newline side index
+    (one binary search), results identical to the oracle; a 64 MiB single-line chunk stays
+    bounded (the unindexed scan would walk up to 64 MiB per hit)."""
+    rng = np.random.default_rng(12)
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "l.idx")
+        w = oracle.Writer(p, 1 << 22)
+        lens = [0, 1, 63, 64, 65, 127, 128, 129, 200, 5000, 70000, 3, 0, 0, 900_000, 64, 1]
+        for ln in lens * 2:
+            w.add_entry(bytes(rng.choice(np.frombuffer(b"abc ", dtype=np.uint8), size=ln)))
+        w.finalize()
+        w.close()
+        r, o = pss.Reader(p), oracle.Reader(p)
+        _compare_searches(r, o, [b"abc", b"a", b"", b"\n", b"cab a", b" ", b"\n\n", b"bbbbbbbb", b"c\na"])
+        for pat in (b"abca", b"zz", b"\n"):
+            _compare_searches(r, o, [pat])
+        r.close()
+        o.close()
+    # one 64 MiB line (2-symbol text: every 2-gram has ~16 M matching suffixes, all in the same entry)
+    n = 64 << 20
+    text = rng.integers(97, 99, size=n, dtype=np.uint8)
+    text[-1] = 10
+    sa = pss.libsais(text)
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "one.idx")
+        with open(p, "wb") as f:
+            f.write(np.uint32(n).tobytes()); f.write(memoryview(text))
+            f.write(np.uint32(4 * n).tobytes()); f.write(memoryview(sa))
+        r = pss.Reader(p)
+        qo, ch, st, en, stats = r.search_batch([b"ab", b"ba"])
+        assert qo.tolist() == [0, 1, 2] and st.tolist() == [0, 0] and en.tolist() == [n - 1, n - 1]
+        assert stats["n_hits"] > n // 3
+        assert stats["ms_extract"] < 50.0, stats       # 33 M hits x one bounded lookup each
+        qo, ch, st, en, stats = r.search_batch([bytes(text[1000:1040])])
+        assert st.tolist() == [0] and en.tolist() == [n - 1]
+        r.close()
+
+
+def test_reader_over_device_resident_chunks(pss, oracle):
+    """pss_reader_open_device_chunks: chunks built and kept in HBM (no file), searched through the
+    same pipeline; with world = 1 the distributed call is the plain search."""
+    import torch
+    texts = [synth.zipf_words_text(1_500_000 + 1000 * k, seed=300 + k, vocab=2048, block=1 << 16) for k in range(3)]
+    d_text, d_sa, chunks = [], [], []
+    builder = C.c_void_p()
+    pss.check(pss.lib.pss_sa_builder_create(-1, 0, C.byref(builder)))
+    for k, t in enumerate(texts):
+        dt = torch.zeros(len(t) + 16, dtype=torch.uint8, device="cuda")
+        dt[:len(t)] = torch.from_numpy(t).cuda()
+        ds = torch.empty(len(t), dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        pss.check(pss.lib.pss_sa_builder_build_device(builder, dt.data_ptr(), len(t), ds.data_ptr(), None))
+        d_text.append(dt); d_sa.append(ds)
+        chunks.append(pss.DeviceChunk(dt.data_ptr(), ds.data_ptr(), t.ctypes.data, len(t), k))
+    pss.lib.pss_sa_builder_destroy(builder)
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "ref.idx")
+        with open(p, "wb") as f:
+            for t, ds in zip(texts, d_sa):
+                f.write(np.uint32(len(t)).tobytes()); f.write(memoryview(t))
+                f.write(np.uint32(4 * len(t)).tobytes()); f.write(memoryview(ds.cpu().numpy()))
+        o = oracle.Reader(p)
+        for k, t in enumerate(texts):
+            assert np.array_equal(o.chunk_sa(k), oracle.suffix_array_port(t))
+        r = pss.Reader(device_chunks=chunks, n_chunks_total=3)
+        pats = synth.config2_queries(texts[1], nq=300, seed=9) + [b"", b"e ", b"\n"]
+        _compare_searches(r, o, pats)
+        comm = pss.Comm(0, 1)
+        qo, ch, st, en, stats = r.search_batch_dist(comm, pats)
+        counts, och, ost, oen = o.search_multiple_tuples(pats)
+        assert np.array_equal(np.diff(qo), counts) and np.array_equal(ch, och)
+        assert np.array_equal(st, ost) and np.array_equal(en, oen)
+        comm.close()
+        r.close()
+        o.close()
+
+
+def test_two_gpu_distributed_search_matches_single_process():
+    """One process per GPU (torchrun, 2 ranks): index sharded chunk k → rank k % 2, batch broadcast
+    from rank 0, hits gathered with the in-library NCCL gather-v; rank 0's merged result must equal
+    the single-process Reader's and the oracle's (tools/dist_check.py asserts it)."""
+    import subprocess
+    import sys
+    from pysubstringsearch_b200 import capi
+    if capi.lib.pss_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from tests.conftest import ROOT
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tools", "dist_check.py")]
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "dist_check ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
 # ------------------------------------------------------------------------------------
