@@ -586,8 +586,9 @@ int RadixSorter::sort(uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, uint32
         if (trivial[p]) continue;  // every key has the same digit: order unchanged
         const int shift     = begin_bit + p * RADIX_BITS;
         const uint32_t mask = (p == npass - 1) ? last_mask : (uint32_t)(RADIX - 1);
-        PSS_CUDA_TRY(cudaMemsetAsync(d_tile_state_, 0, (size_t)tiles * RADIX * sizeof(uint32_t), stream));
+        // the event pair brackets the pass AND the reset of its look-back words (tiles x 1 KiB)
         if (timed) PSS_CUDA_TRY(cudaEventRecord(ev_[2 * executed], stream));
+        PSS_CUDA_TRY(cudaMemsetAsync(d_tile_state_, 0, (size_t)tiles * RADIX * sizeof(uint32_t), stream));
         {
             const uint32_t *vals_arg = iota ? nullptr : vin;
             const uint32_t *base_arg = d_bin_base_ + p * RADIX;

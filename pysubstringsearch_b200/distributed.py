@@ -1,87 +1,86 @@
-"""One-process-per-GPU plumbing for sharded indexes (torch.distributed; NCCL on GPUs, gloo
-on CPU for tests).
+"""One-process-per-GPU plumbing for sharded indexes.
 
 Chunks are the shard unit (the reference already treats them as the parallel
 unit at search time, lib.rs:207): chunk k is owned by rank k % world.  BUILD needs no
-collective.  SEARCH has one exchange step per batch: the packed query batch is broadcast
-from rank 0, every rank searches its own chunks, and the per-chunk hit tuples are gathered
-to rank 0, which orders them by (query, chunk) — the order a single-process Reader returns.
+collective.  SEARCH has one exchange step per batch, and it lives INSIDE libpss_b200.so
+(csrc/dist.cu, NCCL over NVLink): broadcast of the batch from rank 0 → local search →
+gather-v of exactly the tuples found → placement into the single-process order.  This module
+only bootstraps the library's communicator from an existing torch.distributed process group
+(`init_comm`) and restates the placement arithmetic in numpy (`place_reference`) so that the
+host-side logic can be tested on CPU with gloo ranks.
 """
 import numpy as np
-import torch
-import torch.distributed as dist
 
 
 def chunk_owner(chunk, world):
     return chunk % world
 
 
-def broadcast_queries(blob, offsets, device, src=0):
-    """blob: uint8 tensor, offsets: int64 tensor (valid on `src`; other ranks may pass None).
-    Returns (blob, offsets) tensors on `device` on every rank."""
-    rank = dist.get_rank()
-    meta = torch.zeros(2, dtype=torch.int64, device=device)
-    if rank == src:
-        meta[0], meta[1] = blob.numel(), offsets.numel()
-    dist.broadcast(meta, src)
-    nb, no = int(meta[0]), int(meta[1])
-    if rank == src:
-        blob, offsets = blob.to(device).contiguous(), offsets.to(device).contiguous()
-    else:
-        blob = torch.empty(nb, dtype=torch.uint8, device=device)
-        offsets = torch.empty(no, dtype=torch.int64, device=device)
-    dist.broadcast(blob, src)
-    dist.broadcast(offsets, src)
-    return blob, offsets
+def owned_chunks(rank, world, n_total):
+    """Global ids of the chunks rank `rank` holds, ascending (local chunk j ↔ global j * world + rank)."""
+    return list(range(rank, n_total, world))
 
 
-_BUFFERS = {}
+def init_comm():
+    """pss Comm over the current torch.distributed group: rank 0's NCCL id reaches the other
+    ranks through a torch broadcast (works on the nccl and the gloo backend)."""
+    import torch
+    import torch.distributed as dist
+    from . import capi
+    rank, world = dist.get_rank(), dist.get_world_size()
+    on_gpu = dist.get_backend() == "nccl"
+
+    def exchange(raw):
+        t = torch.tensor(list(raw), dtype=torch.uint8, device="cuda" if on_gpu else "cpu")
+        dist.broadcast(t, 0)
+        return bytes(t.cpu().tolist())
+
+    return capi.Comm(rank, world, exchange if world > 1 else None)
 
 
-def _buffer(key, shape, dtype, device):
-    buf = _BUFFERS.get(key)
-    if buf is None or buf.shape != torch.Size(shape) or buf.device != device:
-        buf = torch.empty(shape, dtype=dtype, device=device)
-        _BUFFERS[key] = buf
-    return buf
+def chunks_before(rank, k, world):
+    """Chunks owned by `rank` whose global id is below k (csrc/dist.cu: chunks_before)."""
+    return (k - rank - 1) // world + 1 if k > rank else 0
 
 
-def gather_hits(query, chunk, start, end, dst=0):
-    """Variable-length gather of hit tuples to `dst`.  Inputs: 1-D int32 tensors of equal
-    length on this rank's device (start/end carry uint32 bit patterns).  Returns on `dst` a
-    list with one (4, k_r) int32 tensor per rank (views into a reused buffer: consume them
-    before the next call), elsewhere None.
+def place_reference(entry_offsets, nq, n_total):
+    """numpy restatement of the placement step of csrc/dist.cu.
 
-    Two collectives per batch: an all-gather of the per-rank counts (so every rank agrees
-    on the padded width) and one gather of the padded (4, kmax) blocks.  The staging
-    buffers persist across calls and only grow."""
-    world, rank = dist.get_world_size(), dist.get_rank()
-    dev = query.device
-    n = query.numel()
-    counts_t = _buffer(("counts", world), (world,), torch.int64, dev)
-    mine = _buffer(("mine",), (1,), torch.int64, dev)
-    mine.fill_(n)
-    dist.all_gather_into_tensor(counts_t, mine)
-    counts = counts_t.tolist()
-    kmax = max(max(counts), 1)
-    cap = 1 << (kmax - 1).bit_length()          # power-of-two widths → few reallocations
-    send = _buffer(("send",), (4, cap), torch.int32, dev)
-    send[0, :n], send[1, :n], send[2, :n], send[3, :n] = query, chunk, start, end
-    if rank == dst:
-        recv = _buffer(("recv",), (world, 4, cap), torch.int32, dev)
-        dist.gather(send, list(recv.unbind(0)), dst=dst)
-        return [recv[r, :, :c] for r, c in enumerate(counts)]
-    dist.gather(send, None, dst=dst)
-    return None
+    entry_offsets[r]: uint array [nq * nc_r + 1] — entries of rank r before its pair
+    p = q * nc_r + j (j = local chunk).  Returns (final, query_offsets): final[r][p] is the
+    position in the merged result of the first entry of rank r's pair p, i.e. the number of
+    entries of every rank in pairs that precede (query q, chunk k = j * world + r) in
+    (query, chunk) order; query_offsets[q] = entries before query q."""
+    world = len(entry_offsets)
+    nc = [len(owned_chunks(r, world, n_total)) for r in range(world)]
+    final = []
+    for r in range(world):
+        f = np.zeros(nq * nc[r], dtype=np.int64)
+        for p in range(nq * nc[r]):
+            q, j = divmod(p, nc[r])
+            k = j * world + r
+            f[p] = sum(int(entry_offsets[r2][q * nc[r2] + chunks_before(r2, k, world)]) for r2 in range(world) if nc[r2])
+        final.append(f)
+    qoff = np.array([sum(int(entry_offsets[r][q * nc[r]]) for r in range(world)) for q in range(nq + 1)], dtype=np.int64)
+    return final, qoff
 
 
-def merge_hits(parts):
-    """Per-rank (4, k) tensors → one (4, K) int32 numpy array ordered by (query, chunk),
-    keeping each rank's own order inside a (query, chunk) pair (SA order of first hit)."""
-    cols = [p.cpu().numpy() for p in parts if p.shape[1]]
-    if not cols:
-        return np.zeros((4, 0), dtype=np.int32)
-    allc = np.concatenate(cols, axis=1)
-    seq = np.arange(allc.shape[1])
-    order = np.lexsort((seq, allc[1], allc[0]))
-    return allc[:, order]
+def merge_reference(parts, nq, n_total):
+    """parts[r] = (entry_offsets, start, end) of rank r → (query_offsets, chunk, start, end) in
+    the single-process order, placed exactly as the library's kernel places them."""
+    world = len(parts)
+    final, qoff = place_reference([p[0] for p in parts], nq, n_total)
+    total = int(qoff[-1])
+    chunk = np.zeros(total, dtype=np.int32)
+    start = np.zeros(total, dtype=np.uint32)
+    end = np.zeros(total, dtype=np.uint32)
+    for r, (eo, st, en) in enumerate(parts):
+        nc = len(owned_chunks(r, world, n_total))
+        for p in range(nq * nc):
+            a, b = int(eo[p]), int(eo[p + 1])
+            if b > a:
+                d = int(final[r][p])
+                chunk[d:d + b - a] = (p % nc) * world + r
+                start[d:d + b - a] = st[a:b]
+                end[d:d + b - a] = en[a:b]
+    return qoff, chunk, start, end

@@ -13,10 +13,10 @@ from tools import synth
 
 
 def test_reference_arm_prints_one_json_line():
-    env = dict(os.environ, PSS_BENCH_CPU_SAMPLE=str(1 << 21))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0", "--queries", "300"], cwd=ROOT, env=env, capture_output=True, text=True,
-                         timeout=600)
+                          "--warmup", "0", "--queries", "300", "--size", str(1 << 21), "--chunks", "3"],
+                         cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, out.stdout
@@ -27,6 +27,8 @@ def test_reference_arm_prints_one_json_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] == 1 and cb["value"] == d["value"] and cb["sample"]
     assert "workload" in d["config"] and d["search"]["unit"] == "queries/s" and d["value"] > 0
+    assert d["scaling"] == "strong" and d["config"]["chunks"] == 3 and "selective" in d["config"]["workload"]
+    assert set(d["search"]["single_query_us"]) == {"google", "text_two", "zzzzzz"}
 
 
 def test_reference_arm_other_ranks_exit_quietly():
@@ -47,6 +49,27 @@ def test_synthetic_generators_are_deterministic():
     assert bytes(blob[offs[3]:offs[4]]) == qa[3]
     t = synth.acgt_text(100_000)
     assert set(np.unique(t).tolist()) <= {10, 65, 67, 71, 84} and t[-1] == 10
+
+
+def test_config3_corpus_is_reproducible_from_prefixes():
+    """Chunks of the config-3 corpus share one vocabulary, differ by seed, and a short prefix of a
+    chunk equals the head of the full chunk — what lets every process cut the same query batch."""
+    a = synth.config3_chunk_torch(2, 300_000)
+    b = synth.config3_chunk_torch(2, 100_000, force_newline=False)
+    assert a.numel() == 300_016 and int(a[299_999]) == 10 and not a[300_000:].any()
+    assert bool((a[:100_000] == b[:100_000]).all())
+    c = synth.config3_chunk_torch(3, 100_000, force_newline=False)
+    assert not bool((c[:100_000] == b[:100_000]).all())
+    words = lambda t: set(bytes(t[:100_000].numpy()).replace(b"\n", b" ").split()[1:-1])
+    assert len(words(b) & words(c)) > 100                       # shared vocabulary
+    pre = [synth.config3_chunk_torch(k, 1 << 20, force_newline=False)[:1 << 20] for k in range(3)]
+    q1 = synth.config3_queries(pre, nq=60, chunk_bytes=1 << 20)
+    q2 = synth.config3_queries(pre, nq=60, chunk_bytes=1 << 20)
+    assert q1 == q2 and len(q1) == 60 and all(4 <= len(q) <= 32 for q in q1)
+    hits = [sum(bytes(p.numpy()).count(q) > 0 for p in pre) for q in q1]
+    assert sum(h > 0 for h in hits) >= 50                       # 90 % are cut from the text
+    t0 = synth.config3_chunk(0, 400_000)
+    assert bytes(t0).count(b"text_two") == 159 or bytes(t0).count(b"text_two") > 100
 
 
 def test_selective_queries_have_bounded_hits(oracle):
