@@ -425,6 +425,8 @@ def run_ours(args):
         c = time.perf_counter()
         eb += b - a
         es += c - b2
+        if world > 1:
+            barrier()     # rank 0 still copies the merged result out: the other ranks' next build must not share its PCIe/host path
     barrier()
     e2e_build_s = max_over_ranks(eb / Ke)
     e2e_search_s = max_over_ranks(es / Ke)

@@ -1,6 +1,8 @@
 // build_engine.cu — asynchronous per-GPU build engines (see build_engine.cuh).
 #include "build_engine.cuh"
 
+#include <chrono>
+#include <cstdlib>
 #include <map>
 #include <new>
 
@@ -51,6 +53,9 @@ int BuildEngine::init(int device) {
     device_ = device;
     PSS_CUDA_TRY(cudaSetDevice(device_));
     PSS_CUDA_TRY(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    PSS_CUDA_TRY(cudaStreamCreateWithFlags(&h2d_stream_, cudaStreamNonBlocking));
+    for (Slot &s : slots_) PSS_CUDA_TRY(cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming));
+    if (const char *e = std::getenv("PSS_ENGINE_TRACE")) trace_ = std::atoi(e) != 0;
     return PSS_OK;
 }
 
@@ -61,7 +66,7 @@ void BuildEngine::free_device_memory() {
     for (Slot &s : slots_) {
         cudaFree(s.d_text);
         cudaFree(s.d_sa);
-        s = Slot();
+        s.d_text = nullptr; s.d_sa = nullptr; s.cap = 0;
     }
     h2d_stager_.release();
     d2h_stager_.release();
@@ -97,47 +102,95 @@ int BuildEngine::begin(const uint8_t *h_text, int32_t n, Job **out) {
     return PSS_OK;
 }
 
+int BuildEngine::free_slot() const {
+    for (int i = 0; i < NSLOTS; ++i)
+        if (!slots_[i].busy) return i;
+    return -1;
+}
+
+// Makes slot `si` large enough for the job and issues the upload of its text on the H2D
+// stream; the build waits for slot.uploaded.  Pinned text: one asynchronous DMA.  Pageable
+// text: bounced through the stager by this thread (returns when the host buffer is consumed).
+int BuildEngine::stage(Job *job, int si) {
+    Slot &slot = slots_[si];
+    const int64_t n = job->n;
+    if (n > slot.cap) {
+        cudaFree(slot.d_text);
+        cudaFree(slot.d_sa);
+        slot.d_text = nullptr; slot.d_sa = nullptr; slot.cap = 0;
+        const int64_t cap = std::max<int64_t>(n, 1 << 16);
+        cudaError_t e = cudaMalloc(&slot.d_text, (size_t)cap + 64);
+        if (e == cudaSuccess) e = cudaMalloc(&slot.d_sa, (size_t)cap * sizeof(int32_t));
+        if (e != cudaSuccess) {
+            cudaFree(slot.d_text);
+            slot.d_text = nullptr;
+            return fail(e == cudaErrorMemoryAllocation ? PSS_ERR_NOMEM : PSS_ERR_CUDA,
+                        std::string("device buffers for the chunk: ") + cudaGetErrorString(e));
+        }
+        slot.cap = cap;
+    }
+    if (n > 0) PSS_TRY(h2d_stager_.copy(slot.d_text, job->h_text, (size_t)n, /*to_device=*/true, h2d_stream_));
+    PSS_CUDA_TRY(cudaEventRecord(slot.uploaded, h2d_stream_));
+    return PSS_OK;
+}
+
 void BuildEngine::worker() {
     cudaSetDevice(device_);
     std::unique_lock<std::mutex> lock(mu_);
+    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     while (true) {
         cv_.wait(lock, [&] { return stop_ || !queue_.empty(); });
         if (queue_.empty()) break;
         Job *job = queue_.front();
-        // a free (text, SA) slot: freed by wait() of an earlier job
-        cv_.wait(lock, [&] { return stop_ || !slots_[0].busy || !slots_[1].busy; });
-        if (stop_ && slots_[0].busy && slots_[1].busy) break;
+        int rc = PSS_OK;
+        std::string err;
+        if (!job->staged) {
+            // a free (text, SA) slot: freed by wait() of an earlier job
+            cv_.wait(lock, [&] { return stop_ || free_slot() >= 0; });
+            if (free_slot() < 0) break;
+            job->slot = free_slot();
+            slots_[job->slot].busy = true;
+            lock.unlock();
+            rc = stage(job, job->slot);
+            if (rc != PSS_OK) err = pss_last_error();
+            lock.lock();
+            job->staged = true;
+        }
         queue_.pop_front();
-        const int si = slots_[0].busy ? 1 : 0;
-        Slot &slot = slots_[si];
-        slot.busy  = true;
-        job->slot  = si;
         job->state = 1;
+        // the next chunk's text starts arriving now, while this one is built (pinned sources
+        // only: bouncing a pageable text would hold this thread for tens of milliseconds)
+        Job *next = queue_.empty() ? nullptr : queue_.front();
+        int next_slot = -1;
+        if (next && !next->staged && free_slot() >= 0 && host_is_pinned(next->h_text)) {
+            next_slot = free_slot();
+            slots_[next_slot].busy = true;
+            next->slot = next_slot;
+        }
         lock.unlock();
 
-        int rc = PSS_OK;
-        const int64_t n = job->n;
-        if (n > slot.cap) {
-            cudaFree(slot.d_text);
-            cudaFree(slot.d_sa);
-            slot.d_text = nullptr; slot.d_sa = nullptr; slot.cap = 0;
-            const int64_t cap = std::max<int64_t>(n, 1 << 16);
-            cudaError_t e = cudaMalloc(&slot.d_text, (size_t)cap + 64);
-            if (e == cudaSuccess) e = cudaMalloc(&slot.d_sa, (size_t)cap * sizeof(int32_t));
+        const double t0 = now_ms();
+        if (next_slot >= 0) {
+            int rc2 = stage(next, next_slot);      // asynchronous; a failure is reported by that job
+            lock.lock();
+            next->staged = true;
+            if (rc2 != PSS_OK) { next->rc = rc2; next->err = pss_last_error(); }
+            lock.unlock();
+        }
+        if (rc == PSS_OK && job->rc != PSS_OK) { rc = job->rc; err = job->err; }   // its own prefetch failed earlier
+        Slot &slot = slots_[job->slot];
+        if (rc == PSS_OK && job->n > 0) {
+            cudaError_t e = cudaStreamWaitEvent(builder_.stream(), slot.uploaded, 0);
             if (e != cudaSuccess) {
-                cudaFree(slot.d_text);
-                slot.d_text = nullptr;
-                rc = fail(e == cudaErrorMemoryAllocation ? PSS_ERR_NOMEM : PSS_ERR_CUDA,
-                          std::string("device buffers for the chunk: ") + cudaGetErrorString(e));
+                rc = fail(PSS_ERR_CUDA, std::string("cudaStreamWaitEvent: ") + cudaGetErrorString(e));
             } else {
-                slot.cap = cap;
+                rc = builder_.build_device(slot.d_text, job->n, slot.d_sa, builder_.stream());
             }
+            if (rc != PSS_OK) err = pss_last_error();
         }
-        if (rc == PSS_OK && n > 0) {
-            rc = h2d_stager_.copy(slot.d_text, job->h_text, (size_t)n, /*to_device=*/true, builder_.stream());
-            if (rc == PSS_OK) rc = builder_.build_device(slot.d_text, (int32_t)n, slot.d_sa, builder_.stream());
-        }
-        const std::string err = rc == PSS_OK ? std::string() : std::string(pss_last_error());
+        if (trace_)
+            fprintf(stderr, "[pss engine %d] job n=%d slot=%d: staged+built in %.1f ms (device build %.1f ms)%s\n", device_,
+                    job->n, job->slot, now_ms() - t0, builder_.stats().total_ms, next_slot >= 0 ? " +prefetch" : "");
 
         lock.lock();
         job->rc       = rc;
@@ -164,9 +217,13 @@ int BuildEngine::wait(Job *job, int32_t *h_sa) {
             DeviceGuard guard;
             std::lock_guard<std::mutex> d2h(d2h_mu_);
             cudaSetDevice(device_);
+            const auto t0 = std::chrono::steady_clock::now();
             rc = d2h_stager_.copy(h_sa, slots_[job->slot].d_sa, (size_t)job->n * sizeof(int32_t), /*to_device=*/false,
                                   copy_stream_);
             if (rc != PSS_OK) err = pss_last_error();
+            if (trace_)
+                fprintf(stderr, "[pss engine %d] job n=%d slot=%d: suffix array copied out in %.1f ms\n", device_, job->n,
+                        job->slot, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
         }
     }
     {

@@ -6,10 +6,11 @@
 // so that a Writer can keep ingesting chunk k+1 while chunk k is being built
 // (src/lib.rs:67-124 blocks on libsais inside dump_data) and can spread chunks over GPUs.
 //
-// Per device: one SaBuilder (the 32 B/byte sort workspace), one worker thread that runs
-// H2D(text) → build in request order, and TWO (text, SA) slots in HBM, so that the D2H of
-// chunk k (done by whoever calls wait, on a separate stream) overlaps the H2D + build of
-// chunk k+1.  Engines are process-wide and cached: pss_libsais, the Writers and the async
+// Per device: one SaBuilder (the 32 B/byte sort workspace), one worker thread that runs the
+// builds in request order, and THREE (text, SA) slots in HBM: while chunk k is being built,
+// the text of chunk k+1 is already arriving (separate H2D stream, issued before build k
+// starts) and the suffix array of chunk k-1 is leaving (D2H by whoever calls wait, on a third
+// stream).  Engines are process-wide and cached: pss_libsais, the Writers and the async
 // C ABI all share them; pss_release_cached() frees the idle ones.
 #pragma once
 
@@ -29,7 +30,8 @@ public:
     struct Job {
         const uint8_t *h_text = nullptr;
         int32_t        n = 0;
-        int            slot = -1;
+        int            slot = -1;     // assigned when the text upload is issued
+        bool           staged = false;
         int            state = 0;     // 0 queued, 1 building, 2 built (or failed: rc != 0)
         int            rc = PSS_OK;
         std::string    err;
@@ -47,8 +49,8 @@ public:
     int begin(const uint8_t *h_text, int32_t n, Job **out);
     // Blocks until the build is done, copies the suffix array to h_sa[0..n) (pinned memory
     // is written by DMA directly, pageable memory through the stager) and frees the job.
-    // With two slots per device, at most two builds per device can be past their H2D at any
-    // time: wait for them in begin order.
+    // With three slots per device, at most three builds per device can be past their H2D at
+    // any time: wait for them in begin order.
     int wait(Job *job, int32_t *h_sa);
 
     int device() const { return device_; }
@@ -60,16 +62,23 @@ private:
     void free_device_memory();
 
     struct Slot {
-        uint8_t *d_text = nullptr;
-        int32_t *d_sa = nullptr;
-        int64_t  cap = 0;
-        bool     busy = false;
+        uint8_t    *d_text = nullptr;
+        int32_t    *d_sa = nullptr;
+        int64_t     cap = 0;
+        bool        busy = false;
+        cudaEvent_t uploaded = nullptr;    // the text of the slot's job has arrived
     };
+    static constexpr int NSLOTS = 3;
+
+    int  free_slot() const;                         // call with mu_ held; -1 if none
+    int  stage(Job *job, int si);                   // slot buffers + text upload (mu_ NOT held)
 
     int          device_ = -1;
     SaBuilder    builder_;
-    Slot         slots_[2];
+    Slot         slots_[NSLOTS];
+    cudaStream_t h2d_stream_ = nullptr;    // text uploads (ahead of the build that needs them)
     cudaStream_t copy_stream_ = nullptr;   // D2H of finished suffix arrays
+    bool         trace_ = false;           // PSS_ENGINE_TRACE=1: per-job timings on stderr
     HostStager   h2d_stager_, d2h_stager_;
     std::mutex   d2h_mu_;                  // one wait() copies out at a time (d2h_stager_ is shared)
 

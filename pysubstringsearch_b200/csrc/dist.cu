@@ -10,6 +10,8 @@
 #include <dlfcn.h>
 #include <nccl.h>   // types and prototypes only: the library is bound at run time (see NcclApi)
 
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -75,6 +77,14 @@ const NcclApi &nccl() {
             return ::pss::fail(PSS_ERR_CUDA, std::string(#expr) + ": " + nccl().GetErrorString(_r)); \
     } while (0)
 
+static bool dist_trace() {
+    static const bool on = [] { const char *e = std::getenv("PSS_DIST_TRACE"); return e && std::atoi(e) != 0; }();
+    return on;
+}
+static double wall_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 struct pss_comm {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1, device = 0;
@@ -128,21 +138,34 @@ dist_pair_final_kernel(const RankDesc *__restrict__ desc, int G) {
     d.F[p] = sum;
 }
 
+// largest p in [0, npairs) with E[p] <= i (pairs without entries repeat the offset and are skipped)
+__device__ __forceinline__ uint32_t pair_of_entry(const uint32_t *__restrict__ E, uint32_t npairs, uint32_t i) {
+    uint32_t lo = 0, hi = npairs;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(E + mid) <= i) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
 __global__ void __launch_bounds__(256)
 dist_place_kernel(const RankDesc *__restrict__ desc, int G, int32_t *__restrict__ out_chunk,
                   uint32_t *__restrict__ out_start, uint32_t *__restrict__ out_end) {
     const RankDesc d = desc[blockIdx.y];
     const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t i0 = i & ~31u;                 // the warp's first entry
+    if (i0 >= d.count) return;
+    // One binary search per warp (every lane issues the same loads: one transaction each),
+    // then each lane walks forward from the warp's pair: a warp's 32 consecutive entries span
+    // few pairs.  Long runs of empty pairs fall back to the lane's own search.
+    uint32_t p = pair_of_entry(d.E, d.npairs, i0);
     if (i >= d.count) return;
-    // largest p with E[p] <= i (pairs without entries repeat the offset and are skipped)
-    uint32_t lo = 0, hi = d.npairs;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(d.E + mid) <= i) lo = mid;
-        else hi = mid;
-    }
-    const uint32_t dst = d.F[lo] + (i - __ldg(d.E + lo));
-    out_chunk[dst] = (int32_t)((lo % d.nc) * (uint32_t)G + blockIdx.y);
+    int steps = 0;
+    while (p + 1 < d.npairs && __ldg(d.E + p + 1) <= i && steps < 16) { ++p; ++steps; }
+    if (p + 1 < d.npairs && __ldg(d.E + p + 1) <= i) p = pair_of_entry(d.E, d.npairs, i);
+    const uint32_t dst = d.F[p] + (i - __ldg(d.E + p));
+    out_chunk[dst] = (int32_t)((p % d.nc) * (uint32_t)G + blockIdx.y);
     out_start[dst] = d.start[i];
     out_end[dst]   = d.end[i];
 }
@@ -186,6 +209,7 @@ int dist_search_core(pss_reader *r, pss_comm *c, int32_t nq, int64_t total, Dist
         if (r->searcher.chunks()[j].global_id != j * G + me)
             return fail(PSS_ERR_ARG, "distributed search: chunk map is not chunk k -> rank k % world");
 
+    const double tw0 = wall_ms();
     PSS_CUDA_TRY(cudaEventRecord(r->ev0, s));
     // ---- 1. the batch reaches every GPU -------------------------------------------------
     if (G > 1) PSS_NCCL_TRY(nccl().Broadcast(r->d_pat, r->d_pat, off_bytes + (size_t)total, ncclUint8, 0, c->comm, s));
@@ -206,6 +230,7 @@ int dist_search_core(pss_reader *r, pss_comm *c, int32_t nq, int64_t total, Dist
         return PSS_OK;
     }
     PSS_CUDA_TRY(cudaEventRecord(r->ev1, s));
+    const double tw1 = wall_ms();
 
     // ---- 3. gather-v to rank 0 ----------------------------------------------------------------
     if (me != 0) {
@@ -271,6 +296,7 @@ int dist_search_core(pss_reader *r, pss_comm *c, int32_t nq, int64_t total, Dist
     PSS_LAUNCH_CHECK();
     PSS_CUDA_TRY(cudaMemcpyAsync(h_counts, d_counts, (size_t)G * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     PSS_CUDA_TRY(cudaStreamSynchronize(s));     // the one host read of the exchange: how much each rank sends
+    const double tw2 = wall_ms();
 
     int64_t total_entries = 0, recv_entries = 0;
     uint32_t max_count = 0;
@@ -302,6 +328,8 @@ int dist_search_core(pss_reader *r, pss_comm *c, int32_t nq, int64_t total, Dist
         h_desc[0].count = h_counts[0];
     }
     PSS_CUDA_TRY(cudaMemcpyAsync(d_desc, h_desc, (size_t)G * sizeof(RankDesc), cudaMemcpyHostToDevice, s));
+    if (dist_trace()) PSS_CUDA_TRY(cudaStreamSynchronize(s));
+    const double tw3 = wall_ms();
 
     // ---- 4. placement into (query, chunk, SA order) ------------------------------------------
     int32_t  *f_chunk = r->dist_final.as<int32_t>();
@@ -323,6 +351,10 @@ int dist_search_core(pss_reader *r, pss_comm *c, int32_t nq, int64_t total, Dist
     PSS_CUDA_TRY(cudaEventRecord(r->ev2, s));
     PSS_CUDA_TRY(cudaStreamSynchronize(s));
     PSS_CUDA_TRY(cudaEventElapsedTime(&out->ms_exchange, r->ev1, r->ev2));
+    if (dist_trace())
+        fprintf(stderr, "[pss dist] rank 0: bcast+local search %.3f ms | entry offsets in + counts %.3f ms | %lld tuples in "
+                        "(%.1f MB) %.3f ms | placement %.3f ms | total %.3f ms\n",
+                tw1 - tw0, tw2 - tw1, (long long)recv_entries, recv_entries * 8e-6, tw3 - tw2, wall_ms() - tw3, wall_ms() - tw0);
     out->n_entries   = total_entries;
     out->d_qoff      = r->dist_qoff.as<int64_t>();
     out->d_entry_off = nullptr;          // per-rank arrays only; the merged result is indexed by query
@@ -425,9 +457,12 @@ int32_t pss_reader_search_batch_dist(pss_reader *r, pss_comm *c, const uint8_t *
         PSS_CUDA_TRY(cudaMemcpyAsync(r->d_pat, r->h_pat.p, off_bytes + (size_t)total, cudaMemcpyHostToDevice, s));
     }
     DistOut d;
+    const double th0 = wall_ms();
     PSS_TRY(dist_search_core(r, c, nq, total, &d));
+    const double th1 = wall_ms();
     if (c->rank == 0) {
         PSS_TRY(res->alloc(nq, d.n_entries));
+        const double th2 = wall_ms();
         PSS_CUDA_TRY(cudaMemcpyAsync(res->query_off(), d.d_qoff, off_bytes, cudaMemcpyDeviceToHost, s));
         if (d.n_entries) {
             const size_t b = (size_t)d.n_entries * 4;
@@ -438,6 +473,9 @@ int32_t pss_reader_search_batch_dist(pss_reader *r, pss_comm *c, const uint8_t *
         PSS_CUDA_TRY(cudaEventRecord(ev_end, s));
         PSS_CUDA_TRY(cudaEventSynchronize(ev_end));
         PSS_CUDA_TRY(cudaEventElapsedTime(&res->pub.ms_total, ev_begin, ev_end));
+        if (dist_trace())
+            fprintf(stderr, "[pss dist] rank 0 host call: core %.3f ms | result block %.3f ms | D2H of %lld entries %.3f ms\n",
+                    th1 - th0, th2 - th1, (long long)d.n_entries, wall_ms() - th2);
         if (res->query_off()[nq] != d.n_entries)
             return fail(PSS_ERR_CUDA, "internal error: per-query counts do not add up to the entry count");
         res->publish(d.n_entries);

@@ -736,14 +736,6 @@ namespace {
 constexpr size_t STAGE_SLICE = 16u << 20;
 constexpr size_t STAGE_MIN   = 8u << 20;   // below this a plain cudaMemcpy is as good
 
-bool host_pointer_is_pinned(const void *p) {
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-    }
-    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
-}
 
 void parallel_memcpy(uint8_t *dst, const uint8_t *src, size_t len, int threads) {
     if (threads <= 1 || len < (1u << 20)) {
@@ -768,6 +760,15 @@ int copy_threads() {
 
 }  // namespace
 
+bool host_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
 void HostStager::release() {
     for (int i = 0; i < 2; ++i) {
         if (stage_[i]) cudaFreeHost(stage_[i]);
@@ -781,7 +782,7 @@ void HostStager::release() {
 int HostStager::copy(void *dst, const void *src, size_t bytes, bool to_device, cudaStream_t stream) {
     if (bytes == 0) return PSS_OK;
     const void *host = to_device ? src : dst;
-    if (bytes < STAGE_MIN || host_pointer_is_pinned(host)) {
+    if (bytes < STAGE_MIN || host_is_pinned(host)) {
         PSS_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, stream));
         // pageable + small: the runtime has staged the bytes on return; pinned: the caller's
         // buffer must stay untouched until the stream reaches this point

@@ -28,6 +28,8 @@ namespace pss {
 // suffix array is four times the text.  The stager bounces through two pinned slices itself
 // and moves the slices with several CPU threads while the DMA of the next one is in flight.
 // Pinned callers' buffers are copied directly.
+bool host_is_pinned(const void *p);   // page-locked (cudaMallocHost / cudaHostRegister) or managed memory
+
 class HostStager {
 public:
     HostStager() = default;

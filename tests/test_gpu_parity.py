@@ -613,16 +613,15 @@ def test_python_writer_drop_flushes(oracle):
 
 
 # ------------------------------------------------------------------------------------
-# full size (BASELINE configs[0]: one 500 000 000-byte chunk) — size-independent properties
+# full size: BASELINE configs at their stated sizes
 # ------------------------------------------------------------------------------------
-def test_full_size_config1_properties(pss):
-    """The oracle is too slow at this size, so the 500 MB build is checked through properties
-    that pin a suffix array completely: SA is a permutation of 0..n-1, and for neighbours
-    SA[k-1], SA[k]: T[a] < T[b], or T[a] == T[b] and rank(a+1) < rank(b+1) (past-the-end = -1).
-    The searches are checked against an independent scan of the text."""
-    n = 500_000_000
-    text = synth.config1_text(n)
-    sa = pss.libsais(text)
+def _assert_suffix_array_properties(text, sa):
+    """Pins a suffix array completely without an oracle: SA is a permutation of 0..n-1 (every
+    index exactly once), and for neighbours a = SA[k-1], b = SA[k]: T[a] < T[b], or T[a] == T[b]
+    and rank(a+1) < rank(b+1) (past-the-end = -1)."""
+    n = len(text)
+    assert sa.dtype == np.int32 and len(sa) == n
+    assert int(sa.min()) == 0 and int(sa.max()) == n - 1
     seen = np.zeros(n, dtype=bool)
     seen[sa] = True
     assert seen.all(), "SA is not a permutation"
@@ -637,25 +636,93 @@ def test_full_size_config1_properties(pss):
         ra = np.where(a + 1 < n, isa[np.minimum(a + 1, n - 1)], -1)
         rb = np.where(b + 1 < n, isa[np.minimum(b + 1, n - 1)], -1)
         assert bool(np.all((ta < tb) | ((ta == tb) & (ra < rb)))), "suffixes out of order in [%d, %d)" % (lo, hi)
-    del isa
-    # search on the same index: entries containing the pattern, found independently
-    raw = text.tobytes()
-    nl = np.flatnonzero(text == 10)
-    with tempfile.TemporaryDirectory() as d:
+
+
+def _write_one_chunk(path, text, sa):
+    with open(path, "wb") as f:
+        f.write(np.uint32(len(text)).tobytes()); f.write(memoryview(text))
+        f.write(np.uint32(4 * len(text)).tobytes()); f.write(memoryview(sa))
+
+
+def test_full_size_config1_2_5(pss, oracle):
+    """BASELINE configs[0], [1], [4] on the 500 000 000-byte chunk.  The GPU-built suffix array is
+    pinned by its properties; then, on the GPU-written index file, the ORDERED result tuples of
+    the reference restatement (oracle.Reader, which probes the file as lib.rs does) must equal
+    the GPU reader's for: the config-1 queries, the full 10 000-query config-2 batch, and the
+    config-5 query (the most frequent bigram of the text: millions of matching suffixes)."""
+    n = 500_000_000
+    text = synth.config1_text(n)
+    sa = pss.libsais(text)
+    _assert_suffix_array_properties(text, sa)
+    pats = synth.config2_queries(text, nq=10_000, seed=7)
+    pairs = text[:-1].astype(np.uint16) << 8 | text[1:]
+    top = int(np.bincount(pairs, minlength=1 << 16).argmax())
+    bigram = bytes([top >> 8, top & 255])
+    del pairs
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
         p = os.path.join(d, "full.idx")
-        with open(p, "wb") as f:
-            f.write(np.uint32(n).tobytes()); f.write(memoryview(text))
-            f.write(np.uint32(4 * n).tobytes()); f.write(memoryview(sa))
-        r = pss.Reader(p)
-    for pat in (b"google", b"text_two", b"qqqqqqqqqq"):
-        hits, at = [], raw.find(pat)
-        while at >= 0:
-            hits.append(at)
-            at = raw.find(pat, at + 1)
-        lines = np.unique(np.searchsorted(nl, np.array(hits, dtype=np.int64), side="left")) if hits else np.zeros(0, np.int64)
-        want_start = np.where(lines > 0, nl[np.maximum(lines - 1, 0)] + 1, 0) if len(lines) else np.zeros(0, np.int64)
-        qo, ch, st, en, _ = r.search_batch([pat])
-        assert len(st) == len(lines)
-        assert np.array_equal(np.sort(st.astype(np.int64)), np.sort(want_start))
-        assert np.array_equal(np.sort(en.astype(np.int64)), np.sort(nl[lines])) if len(lines) else len(en) == 0
-    r.close()
+        _write_one_chunk(p, text, sa)
+        del sa
+        r, o = pss.Reader(p), oracle.Reader(p)
+        for pat in (b"google", b"text_two", b"qqqqqqqqqq"):          # config 1
+            _compare_searches(r, o, [pat])
+        qo, ch, st, en, _ = r.search_batch([b"google", b"text_two"])
+        assert np.diff(qo).tolist() == [5943, 159]
+        stats = _compare_searches(r, o, pats)                          # config 2: ordered, full batch
+        assert stats["n_hits"] > 100_000
+        stats = _compare_searches(r, o, [bigram])                      # config 5
+        assert stats["n_hits"] > 5_000_000
+        r.close()
+        o.close()
+
+
+def test_full_size_config3_chunk_and_writer(pss, oracle):
+    """BASELINE configs[2]: (a) one full 2^29-byte chunk of the config-3 corpus: the GPU suffix
+    array equals the reference's own compiled libsais byte for byte; (b) a 3-chunk index written
+    by the GPU Writer from a text file is byte-identical to the oracle Writer's (with the
+    reference libsais), and the sharded readers over it agree with the oracle."""
+    ref = oracle.suffix_array_reference if oracle.reference_libsais_available() else oracle.suffix_array_port
+    text = synth.config3_chunk(1, synth.CONFIG3_CHUNK_BYTES, device="cuda")
+    assert len(text) == 1 << 29 and text[-1] == 10
+    sa = pss.libsais(text)
+    assert np.array_equal(sa, ref(text)), "2^29-byte chunk: suffix array differs from libsais"
+    del sa
+    m = 48 << 20
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
+        src, a, b = os.path.join(d, "in.txt"), os.path.join(d, "gpu.idx"), os.path.join(d, "cpu.idx")
+        with open(src, "wb") as f:
+            for k in range(3):
+                f.write(memoryview(synth.config3_chunk(k, m, device="cuda")))
+        w = pss.Writer(a, m)
+        assert w.add_entries_from_file_lines(src) == 0
+        assert w.close() == 0
+        oracle.use_reference_libsais(oracle.reference_libsais_available())
+        try:
+            ow = oracle.Writer(b, m)
+            ow.add_entries_from_file_lines(src)
+            ow.close()
+        finally:
+            oracle.use_reference_libsais(False)
+        assert os.path.getsize(a) == 3 * (8 + 5 * m)
+        assert subprocess_cmp(a, b), "3-chunk index differs from the oracle Writer's"
+        r, o = pss.Reader(a), oracle.Reader(b)
+        assert r.num_chunks == 3
+        _compare_searches(r, o, [b"google", b"text_two", b"sojq", b"e "] + [bytes(text[k:k + 11]) for k in range(7, 4000, 97)])
+        r.close()
+        o.close()
+
+
+def subprocess_cmp(a, b):
+    import subprocess
+    return subprocess.run(["cmp", "-s", a, b]).returncode == 0
+
+
+def test_full_size_config4_low_entropy(pss):
+    """BASELINE configs[3]: a 2^29-byte ACGT chunk with 64 KiB repeats (the worst case for the
+    doubling depth): permutation + neighbour-order properties of the GPU suffix array."""
+    n = 1 << 29
+    text = synth.acgt_text(n)
+    sa = pss.libsais(text)
+    _assert_suffix_array_properties(text, sa)
+
+
