@@ -85,6 +85,45 @@ __device__ __forceinline__ uint4 ld_stream_u128(const uint4 *p) {
     return v;
 }
 
+// L2 eviction-priority hints (createpolicy + ld/st .L2::cache_hint).  The rank gather / scatter
+// of prefix doubling touches 4 bytes of a window of ISA that fits in L2 while gigabytes of
+// records stream past: without hints the streams (and the 128-byte fills of the random
+// misses themselves) turn L2 over faster than the window is reused (ncu: every ISA line was
+// fetched from DRAM ~18 times).  Window data is marked evict_last, streams evict_first.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint32_t ld_nc_u32_hint(const uint32_t *p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_stream_u32_hint(const uint32_t *p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint4 ld_stream_u128_hint(const uint4 *p, uint64_t pol) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_u32_hint(uint32_t *p, uint32_t v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_u64_hint(uint64_t *p, uint64_t v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
+
 static inline int bit_width_u64(uint64_t v) {
     int b = 0;
     while (v) { ++b; v >>= 1; }

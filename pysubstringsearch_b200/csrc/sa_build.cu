@@ -110,11 +110,12 @@ keygen_kernel(const uint8_t *__restrict__ text, uint32_t n, const uint16_t *__re
 __global__ void __launch_bounds__(256)
 gather_kernel(const uint32_t *__restrict__ idx, const uint32_t *__restrict__ grp,
               const uint32_t *__restrict__ isa, uint32_t n, uint32_t h, int rbits, uint32_t n_active,
-              uint64_t *__restrict__ keys, HistLayout hl, uint32_t *__restrict__ g_hist) {
+              uint64_t *__restrict__ keys, HistLayout hl, uint32_t *__restrict__ g_hist, int l2_hints) {
     constexpr int U = 4;
     __shared__ uint32_t s_hist[MAX_PASSES * RADIX];
     for (int i = threadIdx.x; i < hl.npass * RADIX; i += 256) s_hist[i] = 0;
     __syncthreads();
+    const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first();
     const uint32_t blocks = (n_active + 256 * U - 1) / (256 * U);
     for (uint32_t blk = blockIdx.x; blk < blocks; blk += gridDim.x) {
         const uint32_t base = (blk * 256 * U) + threadIdx.x;
@@ -122,20 +123,25 @@ gather_kernel(const uint32_t *__restrict__ idx, const uint32_t *__restrict__ grp
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             uint32_t k = base + u * 256;
-            i[u] = k < n_active ? ld_stream_u32(idx + k) : 0u;
-            g[u] = k < n_active ? ld_stream_u32(grp + k) : 0u;
+            i[u] = k < n_active ? (l2_hints ? ld_stream_u32_hint(idx + k, stream) : ld_stream_u32(idx + k)) : 0u;
+            g[u] = k < n_active ? (l2_hints ? ld_stream_u32_hint(grp + k, stream) : ld_stream_u32(grp + k)) : 0u;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             uint32_t k = base + u * 256;
             uint64_t j = (uint64_t)i[u] + h;
-            r[u] = (k < n_active && j < n) ? __ldg(isa + j) : 0u;
+            // the active set is bucketed by index window: these reads stay inside a slice of ISA
+            // that fits in L2, provided L2 keeps it (evict_last) while the records stream by
+            r[u] = (k < n_active && j < n) ? (l2_hints ? ld_nc_u32_hint(isa + j, keep) : __ldg(isa + j)) : 0u;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             uint32_t k = base + u * 256;
             const uint64_t kv = ((uint64_t)g[u] << rbits) | r[u];
-            if (k < n_active) keys[k] = kv;
+            if (k < n_active) {
+                if (l2_hints) st_u64_hint(keys + k, kv, stream);
+                else keys[k] = kv;
+            }
             // the warp's 32 keys are consecutive: full iff its last one is in range
             hist_accumulate(s_hist, kv, k < n_active, (k | 31u) < n_active, hl);
         }
@@ -501,6 +507,7 @@ int SaBuilder::init(int device, int64_t max_n) {
         if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);
         cudaGetLastError();
     }
+    if (const char *e = std::getenv("PSS_L2_HINTS")) l2_hints_ = std::atoi(e);
     PSS_CUDA_TRY(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     PSS_CUDA_TRY(cudaEventCreate(&ev_begin_));
     PSS_CUDA_TRY(cudaEventCreate(&ev_end_));
@@ -708,7 +715,7 @@ int SaBuilder::build_device(const uint8_t *d_text, int32_t n, int32_t *d_sa, cud
         {
             const int grid = (int)std::min<int64_t>(div_up(n_active, 256 * 4), (int64_t)sorter_.num_sms() * 8);
             gather_kernel<<<grid, 256, 0, s>>>(v_in, grp_, isa_, un, (uint32_t)std::min<uint64_t>(h, un), rbits, n_active,
-                                               keys_a_, hist_layout(0, rbits + gbits), sorter_.d_hist());
+                                               keys_a_, hist_layout(0, rbits + gbits), sorter_.d_hist(), l2_hints_);
             PSS_LAUNCH_CHECK();
         }
         PSS_TRY(sorter_.sort(keys_a_, keys_b_, v_in, v_alt, n_active, 0, rbits + gbits, /*iota=*/false, s, &in_alt,

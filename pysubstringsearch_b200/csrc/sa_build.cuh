@@ -92,6 +92,7 @@ private:
     cudaEvent_t  ev_begin_ = nullptr, ev_end_ = nullptr;
     HostStager   stager_;                              // pinned bounce slices for pageable callers
     bool         profiling_ = false;
+    int          l2_hints_ = 1;           // PSS_L2_HINTS=0 disables the evict_last / evict_first cache hints
     pss_build_stats stats_ = {};
     std::vector<pss_pass_stat> pass_stats_;
 };

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small driver for ncu: builds one suffix array (and optionally runs a query batch) through the
-C ABI.  usage: profile_build.py [n_bytes] [kind=words|acgt] [search=0|1] [repeat]"""
+C ABI.  usage: profile_build.py [n_bytes] [kind=words|acgt|c3] [search=0|1] [repeat]"""
 import ctypes as C
 import os
 import sys
@@ -17,7 +17,10 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 28
 kind = sys.argv[2] if len(sys.argv) > 2 else "words"
 do_search = len(sys.argv) > 3 and sys.argv[3] == "1"
 repeat = int(sys.argv[4]) if len(sys.argv) > 4 else 1
-text = synth.config1_text(n) if kind == "words" else synth.acgt_text(n)
+if kind == "c3":      # chunk 1 of the config-3 corpus, generated on the GPU (fast)
+    text = synth.config3_chunk(1, n, device="cuda")
+else:
+    text = synth.config1_text(n) if kind == "words" else synth.acgt_text(n)
 sa = np.empty(n, dtype=np.int32)
 b = C.c_void_p()
 pss.check(pss.lib.pss_sa_builder_create(-1, n, C.byref(b)))
@@ -38,6 +41,7 @@ for _ in range(repeat):
             print("  round %d shift %2d spread %5.1f n=%10d %.3f ms %7.1f GB/s" % (q.round, q.shift, q.reserved / 1000.0, q.n_records, q.ms, 24.0 * q.n_records / (q.ms * 1e-3) / 1e9))
 if do_search:
     pats = synth.config2_queries(text, nq=10000, seed=7)
+    pats += [b"sojq", b"google", b"e "]
     with tempfile.TemporaryDirectory() as d:
         p = os.path.join(d, "p.idx")
         with open(p, "wb") as f:
