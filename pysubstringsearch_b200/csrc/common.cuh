@@ -43,6 +43,14 @@ inline void count_launch(int k = 1) { g_kernel_launches.fetch_add(k, std::memory
 int default_device();
 int sm_count(int device);
 
+// Copies a few 32-bit words between device memory and MAPPED pinned host memory with a tiny
+// kernel instead of cudaMemcpyAsync: no copy engine is involved, so the scalar read-backs of
+// a build do not queue behind the multi-gigabyte D2H / H2D of the neighbouring chunk (measured:
+// a build that overlapped a 2 GiB suffix-array copy took 137 ms instead of 96 ms because its
+// first 32-byte read-back waited for that copy on the shared D2H engine).
+int copy_words(uint32_t *dst, const uint32_t *src, int n, cudaStream_t stream);
+int alloc_mapped_words(uint32_t **p, int n);   // cudaHostAlloc(..., cudaHostAllocMapped), zeroed
+
 // ---- device helpers -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ uint32_t lanemask_lt() {

@@ -2,6 +2,7 @@
 #include "radix_sort.cuh"
 
 #include <algorithm>
+#include <cstring>
 
 namespace pss {
 
@@ -18,10 +19,11 @@ constexpr uint32_t FLAG_ABORT = 3u;  // a predecessor gave up (watchdog)
 constexpr uint64_t WATCHDOG_NS = 30ull * 1000ull * 1000ull * 1000ull;
 
 constexpr int CTRL_TICKET  = 0;   // [0..8)
-constexpr int CTRL_ERROR   = 8;
 constexpr int CTRL_TRIVIAL = 16;  // [16..24)
 constexpr int CTRL_MAXBIN  = 24;  // [24..32) digit spread (expected distinct digits per warp x1000)
-constexpr int CTRL_WORDS   = 32;
+constexpr int CTRL_RESET   = 32;  // words [0..32) are cleared by every sort
+constexpr int CTRL_ERROR   = 32;  // sticky look-back watchdog flag (cleared when it is reported)
+constexpr int CTRL_WORDS   = 40;
 
 // ------------------------------------------------------------------------------------
 // Upfront histogram: one read of the keys, all digits at once.
@@ -361,7 +363,24 @@ __global__ void iota_kernel(uint32_t *v, uint32_t n) {
     if (i < n) v[i] = i;
 }
 
+__global__ void copy_words_kernel(uint32_t *dst, const uint32_t *src, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+
 }  // namespace
+
+int copy_words(uint32_t *dst, const uint32_t *src, int n, cudaStream_t stream) {
+    copy_words_kernel<<<1, 128, 0, stream>>>(dst, src, n);
+    PSS_LAUNCH_CHECK();
+    return PSS_OK;
+}
+
+int alloc_mapped_words(uint32_t **p, int n) {
+    PSS_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(p), (size_t)n * sizeof(uint32_t), cudaHostAllocMapped));
+    std::memset(*p, 0, (size_t)n * sizeof(uint32_t));
+    return PSS_OK;
+}
 
 // ------------------------------------------------------------------------------------
 // Host side
@@ -375,7 +394,7 @@ int RadixSorter::init(int device) {
     PSS_CUDA_TRY(cudaMalloc(&d_bin_base_, MAX_PASSES * RADIX * sizeof(uint32_t)));
     PSS_CUDA_TRY(cudaMalloc(&d_ctrl_, CTRL_WORDS * sizeof(uint32_t)));
     PSS_CUDA_TRY(cudaMemset(d_ctrl_, 0, CTRL_WORDS * sizeof(uint32_t)));   // the error flag is sticky across sort_async calls
-    PSS_CUDA_TRY(cudaMallocHost(&h_ctrl_, CTRL_WORDS * sizeof(uint32_t)));
+    PSS_TRY(alloc_mapped_words(&h_ctrl_, CTRL_WORDS));
     for (auto &e : ev_) PSS_CUDA_TRY(cudaEventCreate(&e));
     ev_ready_ = true;
     cfg_ = 0;
@@ -441,7 +460,7 @@ int RadixSorter::partition(uint64_t *keys, uint64_t *keys_alt, uint32_t n, int s
     const uint32_t tiles = (uint32_t)div_up(n, tile_items_);
     const PassConfig &pc = kPassConfigs[cfg_];
     PSS_CUDA_TRY(cudaMemsetAsync(d_hist_, 0, RADIX * sizeof(uint32_t), stream));
-    PSS_CUDA_TRY(cudaMemsetAsync(d_ctrl_, 0, CTRL_WORDS * sizeof(uint32_t), stream));
+    PSS_CUDA_TRY(cudaMemsetAsync(d_ctrl_, 0, CTRL_RESET * sizeof(uint32_t), stream));
     PSS_CUDA_TRY(cudaMemsetAsync(d_tile_state_, 0, (size_t)tiles * RADIX * sizeof(uint32_t), stream));
     int64_t want = div_up(n, (int64_t)HIST_THREADS * HIST_UNROLL);
     int grid     = (int)std::min<int64_t>(want, (int64_t)num_sms_ * 4);
@@ -467,16 +486,27 @@ int RadixSorter::partition(uint64_t *keys, uint64_t *keys_alt, uint32_t n, int s
 
 // Reads back the look-back watchdog flag (synchronises the stream) and clears it.
 int RadixSorter::poll_error(cudaStream_t stream) {
-    PSS_CUDA_TRY(cudaMemcpyAsync(h_ctrl_, d_ctrl_, CTRL_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    PSS_TRY(copy_words(h_ctrl_, d_ctrl_, CTRL_WORDS, stream));
     PSS_CUDA_TRY(cudaStreamSynchronize(stream));
-    if (h_ctrl_[CTRL_ERROR]) {
-        PSS_CUDA_TRY(cudaMemsetAsync(d_ctrl_ + CTRL_ERROR, 0, sizeof(uint32_t), stream));
-        return fail(PSS_ERR_CUDA, "radix sort: look-back watchdog fired");
-    }
-    return PSS_OK;
+    return check_error_word(h_ctrl_[CTRL_ERROR], stream);
 }
 
 const uint32_t *RadixSorter::d_error_flag() const { return d_ctrl_ + CTRL_ERROR; }
+
+// `word`: the error flag as read back by the caller (together with its own scalars).
+int RadixSorter::check_error_word(uint32_t word, cudaStream_t stream) {
+    if (!word) return PSS_OK;
+    PSS_CUDA_TRY(cudaMemsetAsync(d_ctrl_ + CTRL_ERROR, 0, sizeof(uint32_t), stream));
+    return fail(PSS_ERR_CUDA, "radix sort: look-back watchdog fired");
+}
+
+// Per-pass CUDA-event durations of the last timed sort (its events must have completed).
+int RadixSorter::collect_times(SortProfile *prof) {
+    if (!prof || !prof->timed) return PSS_OK;
+    for (int e = 0; e < prof->n_passes; ++e) PSS_CUDA_TRY(cudaEventElapsedTime(&prof->ms[e], ev_[2 * e], ev_[2 * e + 1]));
+    PSS_CUDA_TRY(cudaEventElapsedTime(&prof->hist_ms, ev_[2 * MAX_PASSES], ev_[2 * MAX_PASSES + 1]));
+    return PSS_OK;
+}
 
 int RadixSorter::sort_async(uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, uint32_t *vals_alt, uint32_t n,
                             int begin_bit, int end_bit, bool iota_vals, cudaStream_t stream, bool *in_alt) {
@@ -499,7 +529,7 @@ int RadixSorter::sort_async(uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, 
     const uint32_t tiles     = (uint32_t)div_up(n, tile_items_);
     const PassConfig &pc     = kPassConfigs[cfg_];
     PSS_CUDA_TRY(cudaMemsetAsync(d_hist_, 0, MAX_PASSES * RADIX * sizeof(uint32_t), stream));
-    PSS_CUDA_TRY(cudaMemsetAsync(d_ctrl_, 0, CTRL_ERROR * sizeof(uint32_t), stream));   // tickets only: the error flag is sticky
+    PSS_CUDA_TRY(cudaMemsetAsync(d_ctrl_, 0, CTRL_RESET * sizeof(uint32_t), stream));   // not the sticky error flag
     {
         int64_t want = div_up(n, (int64_t)HIST_THREADS * HIST_UNROLL);
         int grid     = (int)std::min<int64_t>(want, (int64_t)num_sms_ * 4);
@@ -539,7 +569,7 @@ int RadixSorter::hist_reset(cudaStream_t stream) {
 
 int RadixSorter::sort(uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, uint32_t *vals_alt,
                       uint32_t n, int begin_bit, int end_bit, bool iota_vals, cudaStream_t stream,
-                      bool *in_alt, SortProfile *prof, bool hist_done) {
+                      bool *in_alt, SortProfile *prof, bool hist_done, bool defer_check) {
     *in_alt = false;
     const bool timed = prof && prof->timed;
     if (prof) { prof->n_passes = 0; prof->hist_ms = 0.f; }
@@ -556,7 +586,7 @@ int RadixSorter::sort(uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, uint32
     const PassConfig &pc     = kPassConfigs[cfg_];
 
     if (!hist_done) PSS_CUDA_TRY(cudaMemsetAsync(d_hist_, 0, MAX_PASSES * RADIX * sizeof(uint32_t), stream));
-    PSS_CUDA_TRY(cudaMemsetAsync(d_ctrl_, 0, CTRL_WORDS * sizeof(uint32_t), stream));
+    PSS_CUDA_TRY(cudaMemsetAsync(d_ctrl_, 0, CTRL_RESET * sizeof(uint32_t), stream));
     if (timed) PSS_CUDA_TRY(cudaEventRecord(ev_[2 * MAX_PASSES], stream));
     {
         if (!hist_done) {
@@ -569,7 +599,7 @@ int RadixSorter::sort(uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, uint32
         PSS_LAUNCH_CHECK();
     }
     if (timed) PSS_CUDA_TRY(cudaEventRecord(ev_[2 * MAX_PASSES + 1], stream));
-    PSS_CUDA_TRY(cudaMemcpyAsync(h_ctrl_, d_ctrl_, CTRL_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    PSS_TRY(copy_words(h_ctrl_, d_ctrl_, CTRL_WORDS, stream));
     PSS_CUDA_TRY(cudaStreamSynchronize(stream));
 
     uint32_t max_bin[MAX_PASSES];
@@ -615,15 +645,16 @@ int RadixSorter::sort(uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, uint32
         PSS_LAUNCH_CHECK();
     }
 
-    // Watchdog flag (look-back gave up): never expected; surfaces as an error, not a hang.
-    PSS_CUDA_TRY(cudaMemcpyAsync(h_ctrl_, d_ctrl_, CTRL_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    PSS_CUDA_TRY(cudaStreamSynchronize(stream));
-    if (h_ctrl_[CTRL_ERROR]) return fail(PSS_ERR_CUDA, "radix sort: look-back watchdog fired");
     if (prof) prof->n_passes = executed;
-    if (timed) {
-        for (int e = 0; e < executed; ++e) PSS_CUDA_TRY(cudaEventElapsedTime(&prof->ms[e], ev_[2 * e], ev_[2 * e + 1]));
-        PSS_CUDA_TRY(cudaEventElapsedTime(&prof->hist_ms, ev_[2 * MAX_PASSES], ev_[2 * MAX_PASSES + 1]));
-    }
+    // Watchdog flag (look-back gave up): never expected; surfaces as an error, not a hang.
+    // With defer_check the caller reads d_error_flag() at its own next synchronisation
+    // (check_error_word) and fetches the pass timings afterwards (collect_times): the sort
+    // then costs ONE host round trip (the skip mask above).
+    if (defer_check) return PSS_OK;
+    PSS_TRY(copy_words(h_ctrl_, d_ctrl_, CTRL_WORDS, stream));
+    PSS_CUDA_TRY(cudaStreamSynchronize(stream));
+    PSS_TRY(check_error_word(h_ctrl_[CTRL_ERROR], stream));
+    PSS_TRY(collect_times(prof));
     return PSS_OK;
 }
 

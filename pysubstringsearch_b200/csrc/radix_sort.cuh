@@ -94,7 +94,9 @@ public:
     // Synchronises the stream before returning.
     int sort(uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, uint32_t *vals_alt,
              uint32_t n, int begin_bit, int end_bit, bool iota_vals, cudaStream_t stream,
-             bool *in_alt, SortProfile *prof, bool hist_done = false);
+             bool *in_alt, SortProfile *prof, bool hist_done = false, bool defer_check = false);
+    int check_error_word(uint32_t word, cudaStream_t stream);
+    int collect_times(SortProfile *prof);
 
     // For key-producing kernels that fill the histograms themselves: zero them (hist_reset),
     // accumulate into d_hist() with hist_accumulate/hist_flush, then sort(..., hist_done = true).

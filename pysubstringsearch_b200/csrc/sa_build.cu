@@ -14,7 +14,8 @@ namespace {
 // d_small_ layout (32-bit words)
 constexpr int SM_PRESENCE = 0;    // [0..8)   256-bit set of byte values present in the text
 constexpr int SM_SCALARS  = 8;    // [8..16)  [8] = active suffixes after the current re-rank, [9] = tile ticket,
-                                  //          [10] = look-back watchdog flag, [11] = active-set append cursor
+                                  //          [10] = look-back watchdog flag, [11] = active-set append cursor,
+                                  //          [12] = the sorter's watchdog flag (copied in for the read-back)
 constexpr int SM_LUT      = 16;   // [16..144) 256 x u16: byte value → dense code (1..sigma)
 constexpr int SM_WORDS    = 144;
 
@@ -168,6 +169,7 @@ isa_scatter_kernel(const uint64_t *__restrict__ pairs, uint32_t n_pairs, uint32_
     constexpr int U = 4;
     __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_base;
+    __shared__ uint32_t s_idx[256 * U], s_grp[256 * U];   // the CTA's kept records, staged for coalesced appends
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     // blocked: a thread owns U consecutive pairs, so that its kept records are written together
     const uint32_t base = (blockIdx.x * 256 + threadIdx.x) * U;
@@ -208,15 +210,22 @@ isa_scatter_kernel(const uint64_t *__restrict__ pairs, uint32_t n_pairs, uint32_
         tot += t;
     }
     if (threadIdx.x == 0) s_base = tot ? atomicAdd(counter, tot) : 0u;
-    __syncthreads();
-    uint32_t o = s_base + pre + incl - kept;
+    uint32_t o = pre + incl - kept;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         if ((v[u] >> 31) & 1u) {
-            out_idx[o] = (uint32_t)(v[u] >> 32);
-            out_grp[o] = ((uint32_t)v[u] & 0x7FFFFFFFu) - 1u;
+            s_idx[o] = (uint32_t)(v[u] >> 32);
+            s_grp[o] = ((uint32_t)v[u] & 0x7FFFFFFFu) - 1u;
             ++o;
         }
+    }
+    __syncthreads();
+    // the CTA's run [s_base, s_base + tot) is written by consecutive threads: full sectors
+    // instead of one 32-byte sector per 4-byte record
+    const uint32_t gb = s_base;
+    for (uint32_t t = threadIdx.x; t < tot; t += 256) {
+        out_idx[gb + t] = s_idx[t];
+        out_grp[gb + t] = s_grp[t];
     }
 }
 
@@ -287,11 +296,22 @@ struct RerankTile {
 
 __device__ __forceinline__ void rerank_load(RerankTile &t, const uint64_t *__restrict__ keys, uint32_t base,
                                             uint32_t n_active) {
-    for (uint32_t u = threadIdx.x; u < RR_TILE + 2; u += RR_THREADS) {
-        int64_t k = (int64_t)base + u - 1;
-        uint64_t v = 0;
-        if (k >= 0 && k < (int64_t)n_active) v = ld_stream_u64(keys + k);
-        t.k[RerankTile::slot(u)] = v;
+    // all of a thread's loads are issued before the first store to shared memory: one DRAM round
+    // trip per tile instead of nine dependent ones (ncu: a third of the kernel's stall samples sat
+    // on the store that waited for each load in turn)
+    constexpr int PER = (RR_TILE + 2 + RR_THREADS - 1) / RR_THREADS;   // 9: the last round holds the 2 halo words
+    uint64_t v[PER];
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+        const uint32_t u = e * RR_THREADS + threadIdx.x;
+        const int64_t k  = (int64_t)base + u - 1;
+        v[e] = 0;
+        if (u < RR_TILE + 2 && k >= 0 && k < (int64_t)n_active) v[e] = ld_stream_u64(keys + k);
+    }
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+        const uint32_t u = e * RR_THREADS + threadIdx.x;
+        if (u < RR_TILE + 2) t.k[RerankTile::slot(u)] = v[e];
     }
     __syncthreads();
 }
@@ -325,7 +345,7 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
     return v;
 }
 
-__global__ void __launch_bounds__(RR_THREADS)
+__global__ void __launch_bounds__(RR_THREADS, 5)
 rerank_apply_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t n_active,
                     int gs, int first, unsigned long long *tile_state, uint32_t *scalars,
                     uint32_t *__restrict__ isa, uint64_t *__restrict__ pairs_out, int32_t *__restrict__ sa,
@@ -342,7 +362,6 @@ rerank_apply_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
     __syncthreads();
     const uint32_t tile_id = s_tile;
     const uint32_t base    = tile_id * RR_TILE;
-    rerank_load(tile, keys, base, n_active);
 
     static_assert(RR_IPT == 8, "the vector loads/stores below move 8 records per thread");
     uint32_t flags[RR_IPT];
@@ -350,12 +369,14 @@ rerank_apply_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
     const bool full_tile = base + RR_TILE <= n_active;
     if (full_tile) {
         // a thread's 8 suffix indices are 32 contiguous, 32-byte aligned bytes: two 16-byte loads
-        // instead of eight 4-byte ones that would each pull a whole sector for 4 useful bytes
+        // instead of eight 4-byte ones that would each pull a whole sector for 4 useful bytes.
+        // Issued BEFORE the key loads: both streams share one DRAM round trip.
         const uint4 *vp = reinterpret_cast<const uint4 *>(vals + base + threadIdx.x * RR_IPT);
         const uint4 a = ld_stream_u128(vp), b = ld_stream_u128(vp + 1);
         idx[0] = a.x; idx[1] = a.y; idx[2] = a.z; idx[3] = a.w;
         idx[4] = b.x; idx[5] = b.y; idx[6] = b.z; idx[7] = b.w;
     }
+    rerank_load(tile, keys, base, n_active);
     Tup agg = {0, 0, 0};
 #pragma unroll
     for (int e = 0; e < RR_IPT; ++e) {
@@ -382,50 +403,67 @@ rerank_apply_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
         Tup excl = {0, 0, 0};
         bool aborted = false;
         if (tile_id > 0) {
+            // Four 32-tile windows of predecessor states are fetched per L2 round trip.  With P tiles
+            // in flight, a look-back that covers W tiles per round trip tau sustains W / tau tiles per
+            // second once the walk is the critical path (a tile finds its nearest inclusive prefix
+            // about tau * P / W behind): 32 per step capped the kernel at ~2 TB/s (ncu: 13.8 us per
+            // 2048-record tile, stalls on barrier + long scoreboard).
+            constexpr int LBW = 4;
             int64_t basep  = (int64_t)tile_id - 1;
             uint32_t spins = 0;
             uint64_t t0 = 0;
-            while (true) {
-                const int64_t q = basep - lane;
-                unsigned long long w0 = 2ull << 62, w1 = 2ull << 62;   // before tile 0: inclusive identity
-                if (q >= 0) {
-                    w0 = ld_volatile_u64(tile_state + 2 * (size_t)q);
-                    w1 = ld_volatile_u64(tile_state + 2 * (size_t)q + 1);
+            bool done = false;
+            while (!done && !aborted) {
+                unsigned long long w0[LBW], w1[LBW];
+#pragma unroll
+                for (int j = 0; j < LBW; ++j) {
+                    const int64_t q = basep - 32 * j - lane;
+                    w0[j] = 2ull << 62; w1[j] = 2ull << 62;   // before tile 0: inclusive identity
+                    if (q >= 0) {
+                        w0[j] = ld_volatile_u64(tile_state + 2 * (size_t)q);
+                        w1[j] = ld_volatile_u64(tile_state + 2 * (size_t)q + 1);
+                    }
                 }
-                const uint32_t f0 = (uint32_t)(w0 >> 62), f1 = (uint32_t)(w1 >> 62);
-                const bool ready  = f0 != 0 && f0 == f1;
-                const uint32_t m_incl  = __ballot_sync(0xffffffffu, ready && f0 == 2u);
-                const uint32_t m_abort = __ballot_sync(0xffffffffu, f0 == 3u || f1 == 3u);
-                const int k_incl       = m_incl ? __ffs(m_incl) - 1 : 32;
-                const uint32_t need    = k_incl >= 31 ? 0xffffffffu : ((2u << k_incl) - 1u);   // lanes 0..k_incl
-                const uint32_t m_wait  = __ballot_sync(0xffffffffu, !ready) & need;
-                if (m_abort & need) { aborted = true; break; }
-                if (m_wait) {
+                int consumed = 0;
+#pragma unroll
+                for (int j = 0; j < LBW; ++j) {
+                    if (done || aborted || consumed < j) continue;        // an earlier window has to be polled again
+                    const uint32_t f0 = (uint32_t)(w0[j] >> 62), f1 = (uint32_t)(w1[j] >> 62);
+                    const bool ready  = f0 != 0 && f0 == f1;
+                    const uint32_t m_incl  = __ballot_sync(0xffffffffu, ready && f0 == 2u);
+                    const uint32_t m_abort = __ballot_sync(0xffffffffu, f0 == 3u || f1 == 3u);
+                    const int k_incl       = m_incl ? __ffs(m_incl) - 1 : 32;
+                    const uint32_t need    = k_incl >= 31 ? 0xffffffffu : ((2u << k_incl) - 1u);   // lanes 0..k_incl
+                    const uint32_t m_wait  = __ballot_sync(0xffffffffu, !ready) & need;
+                    if (m_abort & need) { aborted = true; continue; }
+                    if (m_wait) continue;                                  // consumed stays at j: re-poll from here
+                    Tup v = {0, 0, 0};
+                    if ((int)lane <= k_incl) {
+                        v.a = (uint32_t)((w0[j] >> 31) & 0x7FFFFFFFu);
+                        v.b = (uint32_t)(w0[j] & 0x7FFFFFFFu);
+                        v.s = (uint32_t)w1[j];
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        Tup y;
+                        y.a = __shfl_xor_sync(0xffffffffu, v.a, o);
+                        y.b = __shfl_xor_sync(0xffffffffu, v.b, o);
+                        y.s = __shfl_xor_sync(0xffffffffu, v.s, o);
+                        v = tup_comb(v, y);
+                    }
+                    excl = tup_comb(excl, v);
+                    consumed = j + 1;
+                    if (k_incl < 32) done = true;
+                }
+                basep -= 32 * consumed;
+                if (!done && !aborted && consumed == 0) {
                     // wall-clock watchdog (warp-uniform: every lane evaluates the same values)
                     if ((++spins & 0x3FFFu) == 0) {
                         const uint64_t now = __shfl_sync(0xffffffffu, global_timer_ns(), 0);
                         if (t0 == 0) t0 = now;
-                        else if (now - t0 > 30ull * 1000ull * 1000ull * 1000ull) { aborted = true; break; }
+                        else if (now - t0 > 30ull * 1000ull * 1000ull * 1000ull) aborted = true;
                     }
-                    continue;
                 }
-                Tup v = {0, 0, 0};
-                if ((int)lane <= k_incl) {
-                    v.a = (uint32_t)((w0 >> 31) & 0x7FFFFFFFu);
-                    v.b = (uint32_t)(w0 & 0x7FFFFFFFu);
-                    v.s = (uint32_t)w1;
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    Tup y;
-                    y.a = __shfl_xor_sync(0xffffffffu, v.a, o);
-                    y.b = __shfl_xor_sync(0xffffffffu, v.b, o);
-                    y.s = __shfl_xor_sync(0xffffffffu, v.s, o);
-                    v = tup_comb(v, y);
-                }
-                excl = tup_comb(excl, v);
-                if (k_incl < 32) break;
-                basep -= 32;
             }
             if (lane == 0) {
                 if (aborted) {
@@ -512,7 +550,7 @@ int SaBuilder::init(int device, int64_t max_n) {
     PSS_CUDA_TRY(cudaEventCreate(&ev_begin_));
     PSS_CUDA_TRY(cudaEventCreate(&ev_end_));
     PSS_CUDA_TRY(cudaMalloc(&d_small_, SM_WORDS * sizeof(uint32_t)));
-    PSS_CUDA_TRY(cudaMallocHost(&h_small_, SM_WORDS * sizeof(uint32_t)));
+    PSS_TRY(alloc_mapped_words(&h_small_, SM_WORDS));
     PSS_TRY(sorter_.init(device_));
     if (max_n > 0) PSS_TRY(ensure(max_n));
     return PSS_OK;
@@ -610,7 +648,7 @@ int SaBuilder::build_device(const uint8_t *d_text, int32_t n, int32_t *d_sa, cud
         presence_kernel<<<std::max(grid, 1), 256, 0, s>>>(d_text, un, d_small_ + SM_PRESENCE);
         PSS_LAUNCH_CHECK();
     }
-    PSS_CUDA_TRY(cudaMemcpyAsync(h_small_, d_small_, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    PSS_TRY(copy_words(h_small_, d_small_, 8, s));
     PSS_CUDA_TRY(cudaStreamSynchronize(s));
     int sigma = 0;
     uint16_t *lut = reinterpret_cast<uint16_t *>(h_small_ + SM_LUT);
@@ -628,7 +666,7 @@ int SaBuilder::build_device(const uint8_t *d_text, int32_t n, int32_t *d_sa, cud
     stats_.sigma = sigma;
     stats_.bits_per_symbol = b;
     stats_.h0 = m;
-    PSS_CUDA_TRY(cudaMemcpyAsync(d_small_ + SM_LUT, h_small_ + SM_LUT, 512, cudaMemcpyHostToDevice, s));
+    PSS_TRY(copy_words(d_small_ + SM_LUT, h_small_ + SM_LUT, 128, s));   // device reads the mapped host words
 
     // ---- round 0: packed-prefix keys, sort, rank ---------------------------------------
     PSS_TRY(sorter_.hist_reset(s));
@@ -660,8 +698,7 @@ int SaBuilder::build_device(const uint8_t *d_text, int32_t n, int32_t *d_sa, cud
     bool in_alt = false;
     stats_.active_per_round[0] = n;
     PSS_TRY(sorter_.sort(keys_a_, keys_b_, vals_a_, vals_b_, un, 0, m * b, /*iota=*/true, s, &in_alt, &prof,
-                         /*hist_done=*/true));
-    record_passes(0, un);
+                         /*hist_done=*/true, /*defer_check=*/true));
 
     uint32_t partition_min = 1u << 22;
     if (const char *e = std::getenv("PSS_PARTITION_MIN")) partition_min = (uint32_t)std::strtoul(e, nullptr, 10);
@@ -692,15 +729,19 @@ int SaBuilder::build_device(const uint8_t *d_text, int32_t n, int32_t *d_sa, cud
                 alt ? k_sorted : k_other, n_active, isa_, v_free, grp_, d_small_ + SM_SCALARS + 3);
             PSS_LAUNCH_CHECK();
         }
-        PSS_CUDA_TRY(cudaMemcpyAsync(h_small_ + SM_SCALARS, d_small_ + SM_SCALARS, 4 * sizeof(uint32_t),
-                                     cudaMemcpyDeviceToHost, s));
+        // ONE read-back per round: active count, this kernel's watchdog and the sorter's (the
+        // sort before and the partition pass above deferred their checks to here)
+        PSS_TRY(copy_words(d_small_ + SM_SCALARS + 4, sorter_.d_error_flag(), 1, s));
+        PSS_TRY(copy_words(h_small_ + SM_SCALARS, d_small_ + SM_SCALARS, 5, s));
         PSS_CUDA_TRY(cudaStreamSynchronize(s));
         if (h_small_[SM_SCALARS + 2]) return fail(PSS_ERR_CUDA, "re-rank: look-back watchdog fired");
-        if (partitioned) PSS_TRY(sorter_.poll_error(s));
+        PSS_TRY(sorter_.check_error_word(h_small_[SM_SCALARS + 4], s));
         n_active = h_small_[SM_SCALARS];
         return PSS_OK;
     };
     PSS_TRY(rerank(true));
+    PSS_TRY(sorter_.collect_times(&prof));
+    record_passes(0, un);
 
     // ---- doubling rounds ------------------------------------------------------------------
     uint64_t h = (uint64_t)m;
@@ -719,12 +760,14 @@ int SaBuilder::build_device(const uint8_t *d_text, int32_t n, int32_t *d_sa, cud
             PSS_LAUNCH_CHECK();
         }
         PSS_TRY(sorter_.sort(keys_a_, keys_b_, v_in, v_alt, n_active, 0, rbits + gbits, /*iota=*/false, s, &in_alt,
-                             &prof, /*hist_done=*/true));
-        record_passes(round, n_active);
+                             &prof, /*hist_done=*/true, /*defer_check=*/true));
+        const uint32_t n_sorted = n_active;
         k_sorted = in_alt ? keys_b_ : keys_a_;
         v_sorted = in_alt ? v_alt : v_in;
         v_free   = in_alt ? v_in : v_alt;
         PSS_TRY(rerank(false));
+        PSS_TRY(sorter_.collect_times(&prof));
+        record_passes(round, n_sorted);
         h *= 2;
     }
     stats_.rounds = round;
