@@ -35,6 +35,8 @@ struct NcclApi {
     decltype(&ncclCommInitRank)   CommInitRank = nullptr;
     decltype(&ncclCommDestroy)    CommDestroy = nullptr;
     decltype(&ncclBroadcast)      Broadcast = nullptr;
+    decltype(&ncclAllGather)      AllGather = nullptr;
+    decltype(&ncclAllReduce)      AllReduce = nullptr;
     decltype(&ncclSend)           Send = nullptr;
     decltype(&ncclRecv)           Recv = nullptr;
     decltype(&ncclGroupStart)     GroupStart = nullptr;
@@ -61,6 +63,7 @@ const NcclApi &nccl() {
         a.name = reinterpret_cast<decltype(a.name)>(dlsym(h, "nccl" #name));        \
         if (!a.name) { a.error = "libnccl.so.2 lacks nccl" #name; return a; }
         PSS_BIND(GetUniqueId) PSS_BIND(CommInitRank) PSS_BIND(CommDestroy) PSS_BIND(Broadcast) PSS_BIND(Send)
+        PSS_BIND(AllGather) PSS_BIND(AllReduce)
         PSS_BIND(Recv) PSS_BIND(GroupStart) PSS_BIND(GroupEnd) PSS_BIND(GetErrorString)
 #undef PSS_BIND
         a.ok = true;
@@ -90,6 +93,15 @@ struct pss_comm {
     int rank = 0, world = 1, device = 0;
     void *h_pinned = nullptr;     // descriptors + counts staging (pinned)
     size_t h_cap = 0;
+    // Fused exchange: rank 0's result arrays [chunk | start | end], `final_cap` entries each, are
+    // one cudaMalloc block exported with CUDA IPC and mapped by every other rank, whose
+    // compaction kernels store their tuples straight into it over NVLink.
+    int       fused = -1;             // -1 not tried yet, 0 unavailable (NCCL gather-v is used), 1 in use
+    uint32_t *final_base = nullptr;   // rank 0: the block; other ranks: its mapping
+    int64_t   final_cap = 0;
+    uint32_t *d_small = nullptr;      // 64 words: handle broadcast, counts, barrier word
+    uint32_t *h_small = nullptr;      // mapped pinned mirror
+    pss::DeviceBuf all_e, f_me, desc_dev, qoff, pairs_all;
 };
 
 namespace {
@@ -138,6 +150,38 @@ dist_pair_final_kernel(const RankDesc *__restrict__ desc, int G) {
     d.F[p] = sum;
 }
 
+// Same as dist_pair_final_kernel for ONE rank's pairs (every rank computes where its own
+// entries go once all entry-offset arrays have been all-gathered).
+__global__ void __launch_bounds__(256)
+dist_pair_final_one_kernel(const RankDesc *__restrict__ desc, int G, int me) {
+    const RankDesc d = desc[me];
+    const uint32_t p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= d.npairs) return;
+    const uint32_t q = p / d.nc, j = p % d.nc;
+    const uint32_t k = j * (uint32_t)G + (uint32_t)me;
+    uint32_t sum = 0;
+    for (int r2 = 0; r2 < G; ++r2) {
+        const RankDesc o = desc[r2];
+        if (o.nc) sum += __ldg(o.E + (size_t)q * o.nc + chunks_before((uint32_t)r2, k, (uint32_t)G));
+    }
+    d.F[p] = sum;
+}
+
+// P[q * n_total + k] = entries of the merged result before (query q, chunk k) — the same sum as
+// F, laid out in (query, chunk) order: the merged result's per-pair entry offsets.
+__global__ void __launch_bounds__(256)
+dist_global_pairs_kernel(const RankDesc *__restrict__ desc, int G, uint32_t nq, uint32_t n_total, uint32_t *__restrict__ P) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i > nq * n_total) return;
+    const uint32_t q = i / n_total, k = i % n_total;      // i == nq * n_total: q = nq, k = 0 → the total
+    uint32_t sum = 0;
+    for (int r2 = 0; r2 < G; ++r2) {
+        const RankDesc o = desc[r2];
+        if (o.nc) sum += __ldg(o.E + (size_t)q * o.nc + chunks_before((uint32_t)r2, k, (uint32_t)G));
+    }
+    P[i] = sum;
+}
+
 // largest p in [0, npairs) with E[p] <= i (pairs without entries repeat the offset and are skipped)
 __device__ __forceinline__ uint32_t pair_of_entry(const uint32_t *__restrict__ E, uint32_t npairs, uint32_t i) {
     uint32_t lo = 0, hi = npairs;
@@ -150,9 +194,9 @@ __device__ __forceinline__ uint32_t pair_of_entry(const uint32_t *__restrict__ E
 }
 
 __global__ void __launch_bounds__(256)
-dist_place_kernel(const RankDesc *__restrict__ desc, int G, int32_t *__restrict__ out_chunk,
-                  uint32_t *__restrict__ out_start, uint32_t *__restrict__ out_end) {
-    const RankDesc d = desc[blockIdx.y];
+dist_place_kernel(const RankDesc *__restrict__ desc, int G, int rank_base, int32_t *out_chunk,
+                  uint32_t *out_start, uint32_t *out_end) {
+    const RankDesc d = desc[rank_base + blockIdx.y];
     const uint32_t i = blockIdx.x * 256 + threadIdx.x;
     const uint32_t i0 = i & ~31u;                 // the warp's first entry
     if (i0 >= d.count) return;
@@ -165,9 +209,21 @@ dist_place_kernel(const RankDesc *__restrict__ desc, int G, int32_t *__restrict_
     while (p + 1 < d.npairs && __ldg(d.E + p + 1) <= i && steps < 16) { ++p; ++steps; }
     if (p + 1 < d.npairs && __ldg(d.E + p + 1) <= i) p = pair_of_entry(d.E, d.npairs, i);
     const uint32_t dst = d.F[p] + (i - __ldg(d.E + p));
-    out_chunk[dst] = (int32_t)((p % d.nc) * (uint32_t)G + blockIdx.y);
+    out_chunk[dst] = (int32_t)((p % d.nc) * (uint32_t)G + (uint32_t)rank_base + blockIdx.y);
     out_start[dst] = d.start[i];
     out_end[dst]   = d.end[i];
+}
+
+// chunk id of every merged entry from the global pair offsets (rank 0 fills this array itself
+// while the other ranks' tuples arrive: a third less NVLink traffic).  One warp per
+// (query, chunk) pair: its entries are one contiguous run.
+__global__ void __launch_bounds__(256)
+dist_fill_chunk_kernel(const uint32_t *__restrict__ P, uint32_t npairs, uint32_t n_total, int32_t *__restrict__ out_chunk) {
+    const uint32_t p = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (p >= npairs) return;
+    const uint32_t a = __ldg(P + p), b = __ldg(P + p + 1);
+    const int32_t chunk = (int32_t)(p % n_total);
+    for (uint32_t i = a + (threadIdx.x & 31u); i < b; i += 32) out_chunk[i] = chunk;
 }
 
 __global__ void __launch_bounds__(256)
@@ -194,6 +250,9 @@ uint32_t owned_chunks(uint32_t rank, uint32_t world, uint32_t n_total) {
     return rank < n_total ? (n_total - rank + world - 1) / world : 0u;
 }
 
+int dist_search_fused(pss_reader *r, pss_comm *c, int32_t nq, int64_t total, DistOut *out);
+int fused_setup(pss_comm *c, cudaStream_t s);
+
 // The whole collective.  On entry the batch is in r->d_pat on rank 0 ([offsets | bytes],
 // enqueued on the reader's stream); on exit rank 0 holds the merged result on the device.
 int dist_search_core(pss_reader *r, pss_comm *c, int32_t nq, int64_t total, DistOut *out) {
@@ -209,6 +268,10 @@ int dist_search_core(pss_reader *r, pss_comm *c, int32_t nq, int64_t total, Dist
         if (r->searcher.chunks()[j].global_id != j * G + me)
             return fail(PSS_ERR_ARG, "distributed search: chunk map is not chunk k -> rank k % world");
 
+    if (G > 1) {
+        if (c->fused < 0) PSS_TRY(fused_setup(c, s));      // collective, first batch only
+        if (c->fused == 1) return dist_search_fused(r, c, nq, total, out);
+    }
     const double tw0 = wall_ms();
     PSS_CUDA_TRY(cudaEventRecord(r->ev0, s));
     // ---- 1. the batch reaches every GPU -------------------------------------------------
@@ -342,7 +405,7 @@ int dist_search_core(pss_reader *r, pss_comm *c, int32_t nq, int64_t total, Dist
         PSS_LAUNCH_CHECK();
     }
     if (max_count) {
-        dist_place_kernel<<<dim3((unsigned)div_up(max_count, 256), (unsigned)G), 256, 0, s>>>(d_desc, G, f_chunk, f_start, f_end);
+        dist_place_kernel<<<dim3((unsigned)div_up(max_count, 256), (unsigned)G), 256, 0, s>>>(d_desc, G, 0, f_chunk, f_start, f_end);
         PSS_LAUNCH_CHECK();
     }
     dist_query_off_kernel<<<(unsigned)div_up((int64_t)nq + 1, 256), 256, 0, s>>>(d_desc, G, (uint32_t)nq,
@@ -358,6 +421,216 @@ int dist_search_core(pss_reader *r, pss_comm *c, int32_t nq, int64_t total, Dist
     out->n_entries   = total_entries;
     out->d_qoff      = r->dist_qoff.as<int64_t>();
     out->d_entry_off = nullptr;          // per-rank arrays only; the merged result is indexed by query
+    out->d_chunk     = f_chunk;
+    out->d_start     = f_start;
+    out->d_end       = f_end;
+    out->n_chunks    = (int32_t)n_total;
+    return PSS_OK;
+}
+
+// ---- fused exchange: compaction kernels store into rank 0's arrays over peer memory --------------
+
+// One NCCL all-reduce of a word as a stream-ordered barrier: when it completes on rank 0,
+// every rank's earlier work on its stream (its compaction kernel, whose peer stores are
+// flushed at kernel end) is done.
+int stream_barrier(pss_comm *c, cudaStream_t s) {
+    PSS_NCCL_TRY(nccl().AllReduce(c->d_small + 32, c->d_small + 33, 1, ncclUint32, ncclSum, c->comm, s));
+    return PSS_OK;
+}
+
+// min over ranks of a host value (collective, synchronises the stream)
+int all_min(pss_comm *c, cudaStream_t s, uint32_t mine, uint32_t *out) {
+    c->h_small[40] = mine;
+    PSS_TRY(copy_words(c->d_small + 40, c->h_small + 40, 1, s));
+    PSS_NCCL_TRY(nccl().AllReduce(c->d_small + 40, c->d_small + 41, 1, ncclUint32, ncclMin, c->comm, s));
+    PSS_TRY(copy_words(c->h_small + 41, c->d_small + 41, 1, s));
+    PSS_CUDA_TRY(cudaStreamSynchronize(s));
+    *out = c->h_small[41];
+    return PSS_OK;
+}
+
+// (Re)allocates rank 0's result block for `entries` tuples and maps it on every rank.
+// Collective; returns PSS_OK with *ok = false when some rank cannot map peer memory.
+int fused_grow(pss_comm *c, cudaStream_t s, int64_t entries, bool *ok) {
+    *ok = false;
+    const int64_t cap = std::max<int64_t>(entries + entries / 2, 1 << 20);
+    // 1. every mapping of the old block goes away before the block itself
+    if (c->rank != 0 && c->final_base) {
+        cudaIpcCloseMemHandle(c->final_base);
+        c->final_base = nullptr;
+    }
+    uint32_t all_ok = 0;
+    PSS_TRY(all_min(c, s, 1u, &all_ok));
+    cudaIpcMemHandle_t handle;
+    static_assert(sizeof(handle) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    uint32_t good = 1;
+    if (c->rank == 0) {
+        cudaFree(c->final_base);
+        c->final_base = nullptr;
+        c->final_cap = 0;
+        if (cudaMalloc(&c->final_base, (size_t)cap * 3 * sizeof(uint32_t)) != cudaSuccess ||
+            cudaIpcGetMemHandle(&handle, c->final_base) != cudaSuccess) {
+            cudaGetLastError();
+            good = 0;
+            std::memset(&handle, 0, sizeof(handle));
+        }
+        std::memcpy(c->h_small, &handle, sizeof(handle));
+        PSS_TRY(copy_words(c->d_small, c->h_small, 16, s));
+    }
+    // 2. the handle reaches every rank
+    PSS_NCCL_TRY(nccl().Broadcast(c->d_small, c->d_small, 64, ncclUint8, 0, c->comm, s));
+    if (c->rank != 0) {
+        PSS_TRY(copy_words(c->h_small, c->d_small, 16, s));
+        PSS_CUDA_TRY(cudaStreamSynchronize(s));
+        std::memcpy(&handle, c->h_small, sizeof(handle));
+        void *mapped = nullptr;
+        if (cudaIpcOpenMemHandle(&mapped, handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            good = 0;
+        } else {
+            c->final_base = static_cast<uint32_t *>(mapped);
+        }
+    }
+    PSS_TRY(all_min(c, s, good, &all_ok));
+    if (!all_ok) {
+        if (c->rank != 0 && c->final_base) cudaIpcCloseMemHandle(c->final_base);
+        if (c->rank == 0) cudaFree(c->final_base);
+        c->final_base = nullptr;
+        c->final_cap = 0;
+        return PSS_OK;
+    }
+    c->final_cap = cap;
+    *ok = true;
+    return PSS_OK;
+}
+
+int fused_setup(pss_comm *c, cudaStream_t s) {
+    c->fused = 0;
+    if (const char *e = std::getenv("PSS_DIST_FUSED"))
+        if (std::atoi(e) == 0) return PSS_OK;
+    PSS_CUDA_TRY(cudaMalloc(&c->d_small, 64 * sizeof(uint32_t)));
+    PSS_CUDA_TRY(cudaMemset(c->d_small, 0, 64 * sizeof(uint32_t)));
+    PSS_TRY(alloc_mapped_words(&c->h_small, 64));
+    bool ok = false;
+    PSS_TRY(fused_grow(c, s, 1 << 20, &ok));
+    c->fused = ok ? 1 : 0;
+    if (dist_trace())
+        fprintf(stderr, "[pss dist] rank %d: fused peer-memory exchange %s\n", c->rank, ok ? "enabled" : "unavailable (NCCL gather-v)");
+    return PSS_OK;
+}
+
+// The whole collective, fused variant.  Same contract as dist_search_core.
+int dist_search_fused(pss_reader *r, pss_comm *c, int32_t nq, int64_t total, DistOut *out) {
+    const int G = c->world, me = c->rank;
+    cudaStream_t s = r->searcher.stream();
+    const size_t off_bytes = ((size_t)nq + 1) * sizeof(int64_t);
+    const uint32_t n_total = (uint32_t)r->chunks.size();
+    const int nc_me = r->searcher.num_chunks();
+    const double tw0 = wall_ms();
+    PSS_CUDA_TRY(cudaEventRecord(r->ev0, s));
+    // ---- 1. the batch reaches every GPU; 2. local search, compaction deferred ---------------------
+    PSS_NCCL_TRY(nccl().Broadcast(r->d_pat, r->d_pat, off_bytes + (size_t)total, ncclUint8, 0, c->comm, s));
+    SearchOutput so;
+    PSS_TRY(r->searcher.search(r->d_pat + off_bytes, reinterpret_cast<const int64_t *>(r->d_pat), nq, s, &so, &out->times,
+                               /*defer_compact=*/true));
+    out->n_hits = so.n_hits;
+    PSS_CUDA_TRY(cudaEventRecord(r->ev1, s));
+    const double tw1 = wall_ms();
+
+    // ---- 3. all-gather of the per-pair entry offsets (fixed size: nq * most chunks per rank + 1) ---
+    std::vector<uint32_t> nc_of(G), np_of(G);
+    uint32_t max_np = 0;
+    for (int q = 0; q < G; ++q) {
+        nc_of[q] = owned_chunks((uint32_t)q, (uint32_t)G, n_total);
+        np_of[q] = (uint32_t)nq * nc_of[q];
+        max_np = std::max(max_np, np_of[q]);
+    }
+    const size_t words = (size_t)max_np + 1;
+    PSS_TRY(c->all_e.ensure((size_t)(G + 1) * words * sizeof(uint32_t)));
+    uint32_t *e_send = c->all_e.as<uint32_t>(), *e_all = e_send + words;
+    PSS_CUDA_TRY(cudaMemcpyAsync(e_send, so.d_entry_off, ((size_t)np_of[me] + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    PSS_NCCL_TRY(nccl().AllGather(e_send, e_all, words, ncclUint32, c->comm, s));
+    PSS_TRY(c->f_me.ensure((size_t)std::max<uint32_t>(np_of[me], 1) * sizeof(uint32_t)));
+    PSS_TRY(c->desc_dev.ensure((size_t)G * sizeof(RankDesc) + 256));
+    const size_t need_h = (size_t)G * sizeof(RankDesc);
+    if (need_h > c->h_cap) {
+        if (c->h_pinned) cudaFreeHost(c->h_pinned);
+        c->h_pinned = nullptr; c->h_cap = 0;
+        PSS_CUDA_TRY(cudaMallocHost(&c->h_pinned, need_h));
+        c->h_cap = need_h;
+    }
+    RankDesc *h_desc = static_cast<RankDesc *>(c->h_pinned), *d_desc = c->desc_dev.as<RankDesc>();
+    for (int q = 0; q < G; ++q) {
+        h_desc[q] = RankDesc();
+        h_desc[q].E = e_all + (size_t)q * words;
+        h_desc[q].nc = nc_of[q];
+        h_desc[q].npairs = np_of[q];
+        h_desc[q].F = q == me ? c->f_me.as<uint32_t>() : nullptr;
+    }
+    PSS_CUDA_TRY(cudaMemcpyAsync(d_desc, h_desc, need_h, cudaMemcpyHostToDevice, s));
+    dist_counts_kernel<<<1, 32, 0, s>>>(d_desc, G, c->d_small + 44);
+    PSS_LAUNCH_CHECK();
+    PSS_TRY(copy_words(c->h_small + 44, c->d_small + 44, G <= 16 ? G : 16, s));
+    PSS_CUDA_TRY(cudaStreamSynchronize(s));      // the one host read of the exchange: entries per rank
+    if (G > 16) return fail(PSS_ERR_ARG, "fused exchange supports up to 16 ranks");
+    int64_t total_entries = 0;
+    for (int q = 0; q < G; ++q) total_entries += c->h_small[44 + q];
+    if (c->h_small[44 + me] != (uint32_t)so.n_entries) return fail(PSS_ERR_CUDA, "distributed search: inconsistent local entry count");
+    if (total_entries >= (1ll << 32)) return fail(PSS_ERR_ARG, "more than 2^32 entries in one batch");
+    const double tw2 = wall_ms();
+    if (total_entries > c->final_cap) {          // every rank sees the same total: the grow step is collective
+        bool ok = false;
+        PSS_TRY(fused_grow(c, s, total_entries, &ok));
+        if (!ok) return fail(PSS_ERR_CUDA, "distributed search: cannot re-map rank 0's result block on every rank");
+    }
+
+    // ---- 4. where this rank's pairs go, then the compaction writes them there (peer stores) ------
+    int32_t  *f_chunk = reinterpret_cast<int32_t *>(c->final_base);
+    uint32_t *f_start = c->final_base + c->final_cap;
+    uint32_t *f_end   = c->final_base + 2 * c->final_cap;
+    if (np_of[me]) {
+        dist_pair_final_one_kernel<<<(unsigned)div_up(np_of[me], 256), 256, 0, s>>>(d_desc, G, me);
+        PSS_LAUNCH_CHECK();
+    }
+    if (so.deferred) {
+        // chunk ids are not sent: rank 0 derives them from the global pair offsets (below)
+        PSS_TRY(r->searcher.compact_deferred(c->f_me.as<uint32_t>(), nullptr, f_start, f_end, s));
+    } else if (so.n_entries) {
+        // oversized batch (several sub-batches were compacted locally): place from the local arrays
+        h_desc[me].E = so.d_entry_off; h_desc[me].start = so.d_start; h_desc[me].end = so.d_end;
+        h_desc[me].count = (uint32_t)so.n_entries;
+        PSS_CUDA_TRY(cudaMemcpyAsync(d_desc + me, h_desc + me, sizeof(RankDesc), cudaMemcpyHostToDevice, s));
+        dist_place_kernel<<<dim3((unsigned)div_up(so.n_entries, 256), 1), 256, 0, s>>>(d_desc, G, me, f_chunk, f_start, f_end);
+        PSS_LAUNCH_CHECK();
+    }
+    if (me == 0 && total_entries) {
+        const uint32_t np_all = (uint32_t)nq * n_total;
+        PSS_TRY(c->pairs_all.ensure(((size_t)np_all + 1) * sizeof(uint32_t)));
+        dist_global_pairs_kernel<<<(unsigned)div_up((int64_t)np_all + 1, 256), 256, 0, s>>>(d_desc, G, (uint32_t)nq, n_total,
+                                                                                           c->pairs_all.as<uint32_t>());
+        PSS_LAUNCH_CHECK();
+        dist_fill_chunk_kernel<<<(unsigned)div_up((int64_t)np_all * 32, 256), 256, 0, s>>>(c->pairs_all.as<uint32_t>(), np_all,
+                                                                                          n_total, f_chunk);
+        PSS_LAUNCH_CHECK();
+    }
+    // ---- 5. everyone's stores have landed ------------------------------------------------------
+    PSS_TRY(stream_barrier(c, s));
+    if (me == 0) {
+        PSS_TRY(c->qoff.ensure(off_bytes));
+        dist_query_off_kernel<<<(unsigned)div_up((int64_t)nq + 1, 256), 256, 0, s>>>(d_desc, G, (uint32_t)nq, c->qoff.as<int64_t>());
+        PSS_LAUNCH_CHECK();
+    }
+    PSS_CUDA_TRY(cudaEventRecord(r->ev2, s));
+    PSS_CUDA_TRY(cudaStreamSynchronize(s));
+    if (me != 0) return PSS_OK;
+    PSS_CUDA_TRY(cudaEventElapsedTime(&out->ms_exchange, r->ev1, r->ev2));
+    if (dist_trace())
+        fprintf(stderr, "[pss dist] rank 0 (fused): bcast+local search %.3f ms | entry offsets all-gathered + counts %.3f ms | "
+                        "%lld entries placed by peer stores + barrier %.3f ms | total %.3f ms\n",
+                tw1 - tw0, tw2 - tw1, (long long)total_entries, wall_ms() - tw2, wall_ms() - tw0);
+    out->n_entries   = total_entries;
+    out->d_qoff      = c->qoff.as<int64_t>();
+    out->d_entry_off = total_entries ? c->pairs_all.as<uint32_t>() : nullptr;   // (query, chunk) order over ALL chunks
     out->d_chunk     = f_chunk;
     out->d_start     = f_start;
     out->d_end       = f_end;
@@ -419,6 +692,16 @@ int32_t pss_comm_destroy(pss_comm *c) {
         nccl().CommDestroy(c->comm);
     }
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    {
+        DeviceGuard guard;
+        cudaSetDevice(c->device);
+        if (c->final_base) {
+            if (c->rank == 0) cudaFree(c->final_base);
+            else cudaIpcCloseMemHandle(c->final_base);
+        }
+        cudaFree(c->d_small);
+        if (c->h_small) cudaFreeHost(c->h_small);
+    }
     delete c;
     return PSS_OK;
 }

@@ -419,6 +419,83 @@ compact_kernel(const uint32_t *__restrict__ flag, const uint32_t *__restrict__ l
     }
 }
 
+// Deferred compaction (the distributed search): first only the output offset of every pair's
+// first entry (pair_first_kernel → entry_offsets_kernel give the per-pair entry offsets without
+// writing a tuple), later compact_place_kernel writes entry i of pair p to pair_dst[p] + i of
+// arrays that may sit in another GPU's memory.
+__global__ void __launch_bounds__(CP_THREADS)
+pair_first_kernel(const uint32_t *__restrict__ flag, const uint32_t *__restrict__ tile_prefix,
+                  const uint32_t *__restrict__ hit_off, uint32_t npairs, uint32_t nhits, uint32_t *__restrict__ pair_first) {
+    __shared__ uint32_t s_warp[CP_THREADS / 32];
+    const uint32_t base = blockIdx.x * CP_TILE + threadIdx.x * CP_IPT;
+    uint32_t fl[CP_IPT];
+    uint32_t c = 0;
+#pragma unroll
+    for (int e = 0; e < CP_IPT; ++e) {
+        fl[e] = (base + e < nhits) ? flag[base + e] : 0u;
+        c += fl[e] >> 31;
+    }
+    uint32_t total;
+    uint32_t o = block_excl_sum_256(c, s_warp, &total) + tile_prefix[blockIdx.x];
+    if (base >= nhits) return;
+    uint32_t p = find_pair(hit_off, npairs, base);
+#pragma unroll
+    for (int e = 0; e < CP_IPT; ++e) {
+        const uint32_t f = base + e;
+        if (f >= nhits) break;
+        while (f >= __ldg(hit_off + p + 1)) ++p;
+        if (f == __ldg(hit_off + p)) pair_first[p] = o;
+        o += fl[e] >> 31;
+    }
+}
+
+__global__ void __launch_bounds__(CP_THREADS)
+compact_place_kernel(const uint32_t *__restrict__ flag, const uint32_t *__restrict__ line_end,
+                     const uint32_t *__restrict__ tile_prefix, const uint32_t *__restrict__ hit_off,
+                     const uint32_t *__restrict__ entry_off, const uint32_t *__restrict__ pair_dst,
+                     const DeviceChunk *__restrict__ chunks, int nc, uint32_t npairs, uint32_t nhits,
+                     int32_t *out_chunk, uint32_t *out_start, uint32_t *out_end) {
+    __shared__ uint32_t s_warp[CP_THREADS / 32];
+    __shared__ uint32_t s_start[CP_TILE], s_end[CP_TILE], s_dst[CP_TILE];
+    __shared__ int32_t  s_chunk[CP_TILE];
+    const uint32_t base = blockIdx.x * CP_TILE + threadIdx.x * CP_IPT;
+    uint32_t fl[CP_IPT];
+    uint32_t c = 0;
+#pragma unroll
+    for (int e = 0; e < CP_IPT; ++e) {
+        fl[e] = (base + e < nhits) ? flag[base + e] : 0u;
+        c += fl[e] >> 31;
+    }
+    uint32_t total;
+    const uint32_t tile_o = tile_prefix[blockIdx.x];
+    uint32_t l = block_excl_sum_256(c, s_warp, &total);     // index among the tile's kept entries
+    if (base < nhits && c) {
+        uint32_t p = find_pair(hit_off, npairs, base);
+#pragma unroll
+        for (int e = 0; e < CP_IPT; ++e) {
+            const uint32_t f = base + e;
+            if (f >= nhits) break;
+            if (fl[e] >> 31) {
+                while (f >= __ldg(hit_off + p + 1)) ++p;
+                s_start[l] = fl[e] & 0x7FFFFFFFu;
+                s_end[l]   = line_end[f];
+                s_dst[l]   = __ldg(pair_dst + p) + (tile_o + l - __ldg(entry_off + p));
+                s_chunk[l] = chunks[p % (uint32_t)nc].global_id;
+                ++l;
+            }
+        }
+    }
+    __syncthreads();
+    // consecutive threads write consecutive entries: runs of one pair are contiguous at the
+    // destination, so the stores leave as full 32-byte sectors (NVLink-friendly)
+    for (uint32_t t = threadIdx.x; t < total; t += CP_THREADS) {
+        const uint32_t d = s_dst[t];
+        if (out_chunk) out_chunk[d] = s_chunk[t];
+        out_start[d] = s_start[t];
+        out_end[d]   = s_end[t];
+    }
+}
+
 // ------------------------------------------------------------------------------------
 // Small-batch path: ONE launch answers a handful of (query, chunk) pairs end to end.
 // CTA p finds pair p's SA range with two concurrent 512-ary searches (lower bound in warps
@@ -900,7 +977,8 @@ int Searcher::search_small(const uint8_t *h_patterns, const int64_t *h_offsets, 
 }
 
 int Searcher::search(const uint8_t *d_patterns, const int64_t *d_offsets, int32_t nq, cudaStream_t stream,
-                     SearchOutput *out, SearchTimes *times) {
+                     SearchOutput *out, SearchTimes *times, bool defer_compact) {
+    deferred_.valid = false;
     if (device_ < 0) return fail(PSS_ERR_ARG, "searcher not initialised");
     if (nq < 0 || !out) return fail(PSS_ERR_ARG, "bad search arguments");
     *out = SearchOutput();
@@ -964,13 +1042,14 @@ int Searcher::search(const uint8_t *d_patterns, const int64_t *d_offsets, int32_
         }
     }
 
+    const bool defer = defer_compact && subs.size() == 1 && subs[0].device_offsets;
     uint32_t entries = 0;          // entries produced so far (all sub-batches)
     uint32_t next_pair = 0;        // entry_off is filled up to here
     float ms_extract = 0.f, ms_dedup = 0.f;
     for (const Sub &sb : subs) {
         PSS_TRY(ensure_hits(sb.nh));
         if ((int64_t)entries + sb.nh >= (1ll << 32)) return fail(PSS_ERR_ARG, "more than 2^32 entries in one batch");
-        PSS_TRY(ensure_out((int64_t)entries + sb.nh, s));   // entries <= matching suffixes: no count needed up front
+        if (!defer) PSS_TRY(ensure_out((int64_t)entries + sb.nh, s));   // entries <= matching suffixes: no count needed up front
         const uint32_t *hit_off = d_hit_off_ + sb.a;
         uint32_t hit_base = 0;
         if (sb.device_offsets) {
@@ -1010,9 +1089,15 @@ int Searcher::search(const uint8_t *d_patterns, const int64_t *d_offsets, int32_
         tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(d_tile_sum_, tiles, d_scalar_ + 2);
         PSS_LAUNCH_CHECK();
         PSS_CUDA_TRY(cudaMemsetAsync(d_pair_first_, 0xFF, (size_t)sb.np * sizeof(uint32_t), s));
-        compact_kernel<<<tiles, CP_THREADS, 0, s>>>(d_flag_, d_end_, d_tile_sum_, hit_off, hit_base, d_chunks_, nc, sb.a,
-                                                    sb.np, nh, d_pair_first_, d_out_chunk_ + entries,
-                                                    d_out_start_ + entries, d_out_end_ + entries);
+        if (defer) {
+            pair_first_kernel<<<tiles, CP_THREADS, 0, s>>>(d_flag_, d_tile_sum_, hit_off, sb.np, nh, d_pair_first_);
+            deferred_.valid = true;
+            deferred_.npairs = sb.np; deferred_.nhits = nh; deferred_.tiles = tiles; deferred_.nc = nc;
+        } else {
+            compact_kernel<<<tiles, CP_THREADS, 0, s>>>(d_flag_, d_end_, d_tile_sum_, hit_off, hit_base, d_chunks_, nc, sb.a,
+                                                        sb.np, nh, d_pair_first_, d_out_chunk_ + entries,
+                                                        d_out_start_ + entries, d_out_end_ + entries);
+        }
         PSS_LAUNCH_CHECK();
         entry_offsets_kernel<<<1, SCAN_THREADS, 0, s>>>(d_pair_first_, sb.np, d_scalar_ + 2, entries, d_entry_off_ + sb.a);
         PSS_LAUNCH_CHECK();
@@ -1045,9 +1130,10 @@ int Searcher::search(const uint8_t *d_patterns, const int64_t *d_offsets, int32_
                                                                                d_query_off_);
     PSS_LAUNCH_CHECK();
     out->n_entries = entries;
-    out->d_chunk   = d_out_chunk_;
-    out->d_start   = d_out_start_;
-    out->d_end     = d_out_end_;
+    out->deferred  = defer;
+    out->d_chunk   = defer ? nullptr : d_out_chunk_;
+    out->d_start   = defer ? nullptr : d_out_start_;
+    out->d_end     = defer ? nullptr : d_out_end_;
     if (times) {
         float ms = 0.f;
         PSS_CUDA_TRY(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
@@ -1055,6 +1141,19 @@ int Searcher::search(const uint8_t *d_patterns, const int64_t *d_offsets, int32_
         times->ms_extract = ms_extract;
         times->ms_dedup   = ms_dedup;
     }
+    return PSS_OK;
+}
+
+int Searcher::compact_deferred(const uint32_t *d_pair_dst, int32_t *d_chunk, uint32_t *d_start, uint32_t *d_end,
+                               cudaStream_t stream) {
+    if (!deferred_.valid) return PSS_OK;      // nothing matched (or nothing was deferred): no tuples to write
+    if (!d_pair_dst || !d_start || !d_end) return fail(PSS_ERR_ARG, "compact_deferred: null destination");
+    cudaStream_t s = stream ? stream : stream_;
+    compact_place_kernel<<<deferred_.tiles, CP_THREADS, 0, s>>>(d_flag_, d_end_, d_tile_sum_, d_hit_off_, d_entry_off_,
+                                                               d_pair_dst, d_chunks_, deferred_.nc, deferred_.npairs,
+                                                               deferred_.nhits, d_chunk, d_start, d_end);
+    PSS_LAUNCH_CHECK();
+    deferred_.valid = false;
     return PSS_OK;
 }
 

@@ -55,6 +55,7 @@ struct SearchOutput {
     const uint32_t *d_end = nullptr;         // [n_entries] offset of the terminating '\n' (line_head, lib.rs:266-269)
     const int64_t  *d_query_off = nullptr;   // [nq + 1] entries before query q
     bool            on_host = false;         // small path: the five arrays are (mapped pinned) HOST pointers
+    bool            deferred = false;        // compaction not run yet (search(..., defer_compact)): d_chunk/start/end are null
 };
 
 // Patterns of a small batch, passed to the fused kernel by value (no H2D copy).
@@ -88,8 +89,20 @@ public:
 
     // d_patterns / d_offsets: device.  Synchronises `stream` before returning (the counts
     // in *out are host values).
+    //
+    // defer_compact: stop before the compaction — the per-pair entry offsets and the entry
+    // count are final, the tuples are not written yet; compact_deferred() then writes them
+    // wherever the caller wants them (another GPU's memory included).  Ignored (normal
+    // compaction, out->deferred = false) when the batch needs more than one sub-batch.
     int search(const uint8_t *d_patterns, const int64_t *d_offsets, int32_t nq, cudaStream_t stream,
-               SearchOutput *out, SearchTimes *times);
+               SearchOutput *out, SearchTimes *times, bool defer_compact = false);
+
+    // Compaction of the last deferred search: entry i of local pair p (i counted inside the
+    // pair, SA order) is written to index d_pair_dst[p] + i of the three output arrays, which
+    // may live in peer memory (kept entries are staged in shared memory and leave the SM in
+    // contiguous runs).  d_chunk may be null.  Asynchronous on `stream`.
+    int compact_deferred(const uint32_t *d_pair_dst, int32_t *d_chunk, uint32_t *d_start, uint32_t *d_end,
+                         cudaStream_t stream);
 
     // Single-launch path for host-side callers: patterns (host) are passed by value.
     // *handled = false when the batch does not qualify (too many pairs / pattern bytes /
@@ -130,6 +143,11 @@ private:
     uint32_t  small_seq_ = 0;
     bool      small_path_ = true;
     cudaEvent_t ev_[8] = {};
+    struct Deferred {
+        bool     valid = false;
+        uint32_t npairs = 0, nhits = 0, tiles = 0;
+        int      nc = 0;
+    } deferred_;
 };
 
 }  // namespace pss
