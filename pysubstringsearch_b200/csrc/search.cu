@@ -665,6 +665,20 @@ small_search_kernel(const DeviceChunk *__restrict__ chunks, int nc, const __grid
     }
     __syncthreads();
 
+    constexpr uint32_t ALL_PAIRS_MAX = 768;
+    if (H <= ALL_PAIRS_MAX) {
+        // few hits (the common single query): an entry's first hit is the one with no earlier hit
+        // (smaller hit index) of the same (pair, entry start) — H^2 / 1024 key compares per thread
+        // in shared memory instead of ~log^2(H) block-wide barriers of the sort below
+        for (uint32_t f = tid; f < H; f += SMALL_THREADS) {
+            const uint64_t mine = s.key[f] >> 13;
+            bool first = true;
+            for (uint32_t g = 0; g < f; ++g)
+                if ((s.key[g] >> 13) == mine) { first = false; break; }
+            if (first) s.start[f] = 0x80000000u | (uint32_t)(mine & 0x3FFFFFFFu);
+        }
+        __syncthreads();
+    } else {
     // bitonic sort by (pair, entry start, hit index); the head of every (pair, entry start)
     // run is the entry's first hit in SA order
     for (uint32_t k = 2; k <= P2; k <<= 1) {
@@ -685,6 +699,7 @@ small_search_kernel(const DeviceChunk *__restrict__ chunks, int nc, const __grid
             s.start[(uint32_t)cur & (SMALL_CAP - 1)] = 0x80000000u | (uint32_t)((cur >> 13) & 0x3FFFFFFFu);
     }
     __syncthreads();
+    }
 
     // compaction in hit order = (query, chunk, SA order)
     constexpr int PER = SMALL_CAP / SMALL_THREADS;

@@ -21,7 +21,7 @@ def declared_symbols():
 
 def test_library_exports_every_declared_symbol(pss):
     syms = declared_symbols()
-    assert len(syms) >= 29
+    assert len(syms) >= 42
     for s in syms:
         assert hasattr(pss.lib, s), "libpss_b200.so does not export %s" % s
 
@@ -73,6 +73,24 @@ def test_writer_host_logic(pss):
         h = C.c_void_p()
         assert pss.lib.pss_writer_open(os.path.join(d, "no/such/dir/x.idx").encode(), -1, C.byref(h)) == -5
         assert w.add_entries_from_file_lines(os.path.join(d, "missing.txt")) == -5
+
+
+def test_new_entry_points_check_their_arguments(pss):
+    """Async build seam, device lists, communicator: argument errors surface as status codes
+    before any device work (no GPU needed)."""
+    h = C.c_void_p()
+    assert pss.lib.pss_sa_build_begin(-1, None, 5, C.byref(h)) == -1
+    assert pss.lib.pss_sa_build_begin(-1, None, -1, C.byref(h)) == -1
+    assert pss.lib.pss_sa_build_wait(None, None) == -1
+    assert pss.lib.pss_release_cached() == 0
+    assert pss.lib.pss_reader_open_devices(b"/nonexistent/x.idx", None, 2, C.byref(h)) == -1
+    assert pss.lib.pss_reader_open_device_chunks(None, 1, 1, -1, C.byref(h)) == -1
+    assert pss.lib.pss_comm_create(None, 3, 2, C.byref(h)) == -1
+    assert pss.lib.pss_comm_create(None, 0, 0, C.byref(h)) == -1
+    if not HAVE_GPU:
+        buf = (C.c_uint8 * 4)(97, 98, 99, 10)
+        assert pss.lib.pss_sa_build_begin(-1, buf, 4, C.byref(h)) == -3 and "no CUDA device" in pss.err()
+        assert pss.lib.pss_comm_create(None, 0, 1, C.byref(h)) == -3
 
 
 def test_python_module_surface():
@@ -132,6 +150,12 @@ int main(void) {
     printf("pss_build_stats %zu\n", sizeof(pss_build_stats));
     P(pss_build_stats, n_kernel_launches); P(pss_build_stats, active_per_round); P(pss_build_stats, total_ms);
     P(pss_build_stats, records_sorted);
+    P(pss_result, ms_exchange); P(pss_result, n_ranks);
+    printf("pss_device_chunk %zu\n", sizeof(pss_device_chunk));
+    P(pss_device_chunk, d_sa); P(pss_device_chunk, h_text); P(pss_device_chunk, n); P(pss_device_chunk, global_id);
+    printf("pss_device_result %zu\n", sizeof(pss_device_result));
+    P(pss_device_result, n_chunks); P(pss_device_result, n_entries); P(pss_device_result, d_query_offsets);
+    P(pss_device_result, d_entry_offsets); P(pss_device_result, d_line_end); P(pss_device_result, ms_exchange);
     return 0;
 }
 '''
@@ -140,7 +164,8 @@ int main(void) {
         open(c, "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         got = dict(line.rsplit(" ", 1) for line in subprocess.check_output([exe], text=True).splitlines())
-    mirrors = {"pss_result": pss.Result, "pss_pass_stat": pss.PassStat, "pss_build_stats": pss.BuildStats}
+    mirrors = {"pss_result": pss.Result, "pss_pass_stat": pss.PassStat, "pss_build_stats": pss.BuildStats,
+               "pss_device_chunk": pss.DeviceChunk, "pss_device_result": pss.DeviceResult}
     for key, val in got.items():
         if "." in key:
             struct, field = key.split(".")
