@@ -701,13 +701,22 @@ small_search_kernel(const DeviceChunk *__restrict__ chunks, int nc, const __grid
     __syncthreads();
     }
 
-    // compaction in hit order = (query, chunk, SA order)
+    // compaction in hit order = (query, chunk, SA order).  The kept tuples are first packed in
+    // shared memory (the sort keys are dead by now) and then written by consecutive threads:
+    // `out` is host memory behind PCIe, where one 128-byte store per warp instead of 32
+    // scattered 4-byte ones is the difference between ~15 and ~500 bus transactions per array.
     constexpr int PER = SMALL_CAP / SMALL_THREADS;
+    uint32_t *st_start = reinterpret_cast<uint32_t *>(s.key);
+    uint32_t *st_end   = st_start + SMALL_CAP;
     const uint32_t base = tid * PER;
     uint32_t kept = 0;
+    uint32_t vs[PER], ve[PER];
 #pragma unroll
-    for (int e = 0; e < PER; ++e)
-        if (base + e < H) kept += s.start[base + e] >> 31;
+    for (int e = 0; e < PER; ++e) {
+        vs[e] = (base + e < H) ? s.start[base + e] : 0u;
+        ve[e] = (base + e < H) ? s.end[base + e] : 0u;
+        kept += vs[e] >> 31;
+    }
     uint32_t incl = kept;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -715,7 +724,7 @@ small_search_kernel(const DeviceChunk *__restrict__ chunks, int nc, const __grid
         if (lane >= (uint32_t)o) incl += y;
     }
     if (lane == 31) s.warp_sum[warp] = incl;
-    __syncthreads();
+    __syncthreads();                            // also: every thread has read its sort keys / flags
     uint32_t pre = 0, tot = 0;
     for (uint32_t w = 0; w < SMALL_THREADS / 32; ++w) {
         const uint32_t t = s.warp_sum[w];
@@ -731,28 +740,35 @@ small_search_kernel(const DeviceChunk *__restrict__ chunks, int nc, const __grid
             const uint32_t f = base + e;
             if (f >= H) break;
             while (s.off[p + 1] <= f) ++p;
-            const uint32_t v = s.start[f];
-            if (v >> 31) {
-                o_chunk[o] = chunks[p % (uint32_t)nc].global_id;
-                o_start[o] = v & 0x7FFFFFFFu;
-                o_end[o]   = s.end[f];
+            if (vs[e] >> 31) {
+                st_start[o] = vs[e] & 0x7FFFFFFFu;
+                st_end[o]   = ve[e];
                 atomicAdd(&s.pair_entries[p], 1u);
                 ++o;
             }
         }
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0) {                             // entries before every pair (reuses s.off: the hit offsets are dead)
         uint32_t run = 0;
         for (uint32_t p = 0; p < npairs; ++p) {
-            if (p % (uint32_t)nc == 0) hdr->query_off[p / (uint32_t)nc] = run;
-            hdr->entry_off[p] = run;
-            run += s.pair_entries[p];
+            const uint32_t c = s.pair_entries[p];
+            s.off[p] = run;
+            run += c;
         }
-        hdr->entry_off[npairs] = run;
-        hdr->query_off[npairs / (uint32_t)nc] = run;
-        hdr->status = 0; hdr->n_hits = H; hdr->n_entries = tot;
+        s.off[npairs] = run;
     }
+    __syncthreads();
+    for (uint32_t t = tid; t < tot; t += SMALL_THREADS) {
+        uint32_t p = 0;
+        while (s.off[p + 1] <= t) ++p;          // <= 64 pairs
+        o_chunk[t] = chunks[p % (uint32_t)nc].global_id;
+        o_start[t] = st_start[t];
+        o_end[t]   = st_end[t];
+    }
+    if (tid <= npairs) hdr->entry_off[tid] = s.off[tid];
+    if (tid <= npairs / (uint32_t)nc) hdr->query_off[tid] = s.off[tid * (uint32_t)nc];
+    if (tid == 0) { hdr->status = 0; hdr->n_hits = H; hdr->n_entries = tot; }
     __syncthreads();
     if (tid == 0) {
         __threadfence_system();                 // tuples + header fields are visible to the host first
