@@ -92,32 +92,63 @@ bounds_kernel(const DeviceChunk *__restrict__ chunks, int nc, const uint8_t *__r
 // ------------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 1024;
 
+// Dedup tiers by the number of matching suffixes h of a (query, chunk) pair:
+//   light   h <= LIGHT_MAX    one warp, all-pairs compare in shared memory    (pair_dedup_kernel)
+//   medium  h <= MEDIUM_MAX   one CTA, hash set of entry starts in shared memory (pair_dedup_hash_kernel:
+//                             32 KB tables for h <= 2048, a persistent second launch with 128 KB tables above)
+//   heavy   above             global stable sort of (pair, entry start)        (sort_async + mark_kernel)
+constexpr uint32_t LIGHT_MAX  = 256;
+constexpr uint32_t MEDIUM_MAX = 8192;
+
 // hit_off[p] = sum of cnt[0..p) (u32, wraps only when the batch is oversized, which the
-// u64 total reveals); hit_off[npairs] = total.
+// u64 total reveals); hit_off[npairs] = total.  heavy_off[p] = the same scan over the heavy
+// pairs only (where pair p's hits go in the sort's input); med_list = the medium pairs, in order.
+// totals[0] = all hits, totals[1] = hits of heavy pairs, totals[2] = number of medium pairs.
 __global__ void __launch_bounds__(SCAN_THREADS)
 hit_offsets_kernel(const uint32_t *__restrict__ cnt, uint32_t npairs, uint32_t *__restrict__ hit_off,
-                   unsigned long long *__restrict__ total_out) {
-    __shared__ unsigned long long s_part[SCAN_THREADS];
+                   uint32_t *__restrict__ heavy_off, uint32_t *__restrict__ med_list,
+                   unsigned long long *__restrict__ totals) {
+    __shared__ unsigned long long s_part[SCAN_THREADS], s_heavy[SCAN_THREADS];
+    __shared__ uint32_t s_med[SCAN_THREADS];
     const uint32_t per = (npairs + SCAN_THREADS - 1) / SCAN_THREADS;
     const uint32_t lo  = min(npairs, threadIdx.x * per), hi = min(npairs, lo + per);
-    unsigned long long sum = 0;
-    for (uint32_t p = lo; p < hi; ++p) sum += cnt[p];
-    s_part[threadIdx.x] = sum;
+    unsigned long long sum = 0, hsum = 0;
+    uint32_t msum = 0;
+    for (uint32_t p = lo; p < hi; ++p) {
+        const uint32_t c = cnt[p];
+        sum += c;
+        if (c > MEDIUM_MAX) hsum += c;
+        else if (c > LIGHT_MAX) ++msum;
+    }
+    s_part[threadIdx.x]  = sum;
+    s_heavy[threadIdx.x] = hsum;
+    s_med[threadIdx.x]   = msum;
     __syncthreads();
     for (int o = 1; o < SCAN_THREADS; o <<= 1) {
         unsigned long long y = threadIdx.x >= (uint32_t)o ? s_part[threadIdx.x - o] : 0ull;
+        unsigned long long z = threadIdx.x >= (uint32_t)o ? s_heavy[threadIdx.x - o] : 0ull;
+        uint32_t w = threadIdx.x >= (uint32_t)o ? s_med[threadIdx.x - o] : 0u;
         __syncthreads();
         s_part[threadIdx.x] += y;
+        s_heavy[threadIdx.x] += z;
+        s_med[threadIdx.x] += w;
         __syncthreads();
     }
-    unsigned long long run = s_part[threadIdx.x] - sum;
+    unsigned long long run = s_part[threadIdx.x] - sum, hrun = s_heavy[threadIdx.x] - hsum;
+    uint32_t mrun = s_med[threadIdx.x] - msum;
     for (uint32_t p = lo; p < hi; ++p) {
-        hit_off[p] = (uint32_t)run;
-        run += cnt[p];
+        const uint32_t c = cnt[p];
+        hit_off[p]   = (uint32_t)run;
+        heavy_off[p] = (uint32_t)hrun;
+        run += c;
+        if (c > MEDIUM_MAX) hrun += c;
+        else if (c > LIGHT_MAX) med_list[mrun++] = p;
     }
     if (threadIdx.x == SCAN_THREADS - 1) {
         hit_off[npairs] = (uint32_t)s_part[SCAN_THREADS - 1];
-        *total_out      = s_part[SCAN_THREADS - 1];
+        totals[0]       = s_part[SCAN_THREADS - 1];
+        totals[1]       = s_heavy[SCAN_THREADS - 1];
+        totals[2]       = s_med[SCAN_THREADS - 1];
     }
 }
 
@@ -315,18 +346,133 @@ __device__ __forceinline__ void entry_bounds(const DeviceChunk &ch, uint32_t pos
 
 __global__ void __launch_bounds__(256)
 extract_kernel(const DeviceChunk *__restrict__ chunks, int nc, uint32_t pair_base, uint32_t npairs,
-               const uint32_t *__restrict__ hit_off, uint32_t hit_base, const uint32_t *__restrict__ lb, uint32_t nhits,
-               int sbits, uint64_t *__restrict__ keys, uint32_t *__restrict__ line_end) {
+               const uint32_t *__restrict__ hit_off, const uint32_t *__restrict__ heavy_off,
+               const uint32_t *__restrict__ lb, const uint32_t *__restrict__ cnt, uint32_t nhits, int sbits,
+               uint32_t *__restrict__ line_start, uint32_t *__restrict__ line_end,
+               uint64_t *__restrict__ heavy_keys, uint32_t *__restrict__ heavy_vals) {
     const uint32_t f = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t f0 = f & ~31u;               // the warp's first hit
+    if (f0 >= nhits) return;
+    // one binary search per warp (uniform loads), then every lane walks forward from the warp's
+    // pair: 32 consecutive hits span few pairs; long runs of empty pairs fall back to a search
+    uint32_t p = find_pair(hit_off, npairs, f0);
     if (f >= nhits) return;
-    const uint32_t p    = find_pair(hit_off, npairs, f + hit_base);
+    int steps = 0;
+    while (__ldg(hit_off + p + 1) <= f && steps < 16) { ++p; ++steps; }
+    if (__ldg(hit_off + p + 1) <= f) p = find_pair(hit_off, npairs, f);
     const uint32_t pair = pair_base + p;
     const DeviceChunk ch = chunks[pair % (uint32_t)nc];
-    const uint32_t pos  = (uint32_t)__ldg(ch.sa + __ldg(lb + pair) + (f + hit_base - __ldg(hit_off + p)));
+    const uint32_t k    = f - __ldg(hit_off + p);
+    const uint32_t pos  = (uint32_t)__ldg(ch.sa + __ldg(lb + pair) + k);
     uint32_t b, e;
     entry_bounds(ch, pos, &b, &e);
-    keys[f]     = ((uint64_t)p << sbits) | b;
-    line_end[f] = e;
+    line_start[f] = b;
+    line_end[f]   = e;
+    if (__ldg(cnt + pair) > MEDIUM_MAX) {     // heavy pair: its hits also go to the sort's input
+        const uint32_t j = __ldg(heavy_off + p) + k;
+        heavy_keys[j] = ((uint64_t)p << sbits) | b;
+        heavy_vals[j] = f;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// dedup of light pairs: one warp per (query, chunk) pair with at most LIGHT_MAX matching
+// suffixes.  A hit is kept iff no earlier hit of the pair (SA order) has the same entry
+// start (lib.rs:262,274: the first hit in SA order stands for the entry).  The pair's entry
+// starts sit in shared memory; every lane checks its hits against all earlier ones —
+// O(h^2 / 32) compares per lane and no global sort for the bulk of a batch.
+// ------------------------------------------------------------------------------------
+constexpr int PD_WARPS = 8;
+
+__global__ void __launch_bounds__(PD_WARPS * 32)
+pair_dedup_kernel(const uint32_t *__restrict__ hit_off, const uint32_t *__restrict__ cnt, uint32_t pair_base,
+                  uint32_t npairs, const uint32_t *__restrict__ line_start, uint32_t *__restrict__ flag) {
+    __shared__ uint32_t s_start[PD_WARPS][LIGHT_MAX];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t p = blockIdx.x * PD_WARPS + warp;
+    if (p >= npairs) return;
+    const uint32_t h = __ldg(cnt + pair_base + p);
+    if (h == 0 || h > LIGHT_MAX) return;
+    const uint32_t off = __ldg(hit_off + p);
+    uint32_t *st = s_start[warp];
+    for (uint32_t i = lane; i < h; i += 32) st[i] = line_start[off + i];
+    __syncwarp();
+    for (uint32_t i = lane; i < h; i += 32) {
+        const uint32_t mine = st[i];
+        bool first = true;
+        for (uint32_t g = 0; g < i; ++g)
+            if (st[g] == mine) { first = false; break; }
+        flag[off + i] = first ? (0x80000000u | mine) : 0u;
+    }
+}
+
+// dedup of medium pairs: one CTA per pair, a hash set of the pair's entry starts in shared
+// memory (open addressing, at most half full) keeps the smallest hit index per entry start;
+// a hit is kept iff it is that smallest index.  O(h) per pair instead of a sort.
+constexpr int PH_THREADS = 512;
+constexpr uint32_t PH_SMALL_MAX = 2048;            // pairs up to here use the 32 KB table (several CTAs per SM)
+
+__device__ __forceinline__ void hash_dedup_pair(uint32_t *keys, uint32_t *best, uint32_t h, uint32_t off,
+                                                const uint32_t *__restrict__ line_start, uint32_t *__restrict__ flag) {
+    uint32_t bits = 9;                                              // table of at least 512 slots, >= 2h
+    while ((1u << bits) < 2 * h) ++bits;
+    const uint32_t size = 1u << bits, mask = size - 1u;
+    for (uint32_t i = threadIdx.x; i < size; i += PH_THREADS) { keys[i] = 0xFFFFFFFFu; best[i] = 0xFFFFFFFFu; }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < h; i += PH_THREADS) {
+        const uint32_t st = line_start[off + i];
+        uint32_t slot = (st * 2654435761u) >> (32 - bits);
+        while (true) {
+            const uint32_t prev = atomicCAS(&keys[slot], 0xFFFFFFFFu, st);
+            if (prev == 0xFFFFFFFFu || prev == st) { atomicMin(&best[slot], i); break; }
+            slot = (slot + 1) & mask;
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < h; i += PH_THREADS) {
+        const uint32_t st = line_start[off + i];
+        uint32_t slot = (st * 2654435761u) >> (32 - bits);
+        while (keys[slot] != st) slot = (slot + 1) & mask;
+        flag[off + i] = best[slot] == i ? (0x80000000u | st) : 0u;
+    }
+    __syncthreads();
+}
+
+// One CTA per medium pair.  Pairs above PH_SMALL_MAX are only queued (big_list) for the second,
+// persistent launch, which owns a table four times as large.
+__global__ void __launch_bounds__(PH_THREADS)
+pair_dedup_hash_kernel(const uint32_t *__restrict__ med_list, const uint32_t *__restrict__ hit_off,
+                       const uint32_t *__restrict__ cnt, uint32_t pair_base, const uint32_t *__restrict__ line_start,
+                       uint32_t *__restrict__ flag, uint32_t *__restrict__ big_list, uint32_t *__restrict__ big_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t p = med_list[blockIdx.x];
+    const uint32_t h = __ldg(cnt + pair_base + p);
+    if (h > PH_SMALL_MAX) {
+        if (threadIdx.x == 0) big_list[atomicAdd(big_count, 1u)] = p;
+        return;
+    }
+    uint32_t *keys = reinterpret_cast<uint32_t *>(smem_raw);      // entry start, 0xFFFFFFFF = empty
+    hash_dedup_pair(keys, keys + 2 * PH_SMALL_MAX, h, __ldg(hit_off + p), line_start, flag);
+}
+
+__global__ void __launch_bounds__(PH_THREADS)
+pair_dedup_hash_big_kernel(const uint32_t *__restrict__ big_list, const uint32_t *__restrict__ big_count,
+                           uint32_t *__restrict__ cursor, const uint32_t *__restrict__ hit_off,
+                           const uint32_t *__restrict__ cnt, uint32_t pair_base, const uint32_t *__restrict__ line_start,
+                           uint32_t *__restrict__ flag) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_next;
+    uint32_t *keys = reinterpret_cast<uint32_t *>(smem_raw);
+    const uint32_t total = *big_count;
+    while (true) {
+        if (threadIdx.x == 0) s_next = atomicAdd(cursor, 1u);
+        __syncthreads();
+        const uint32_t j = s_next;
+        __syncthreads();
+        if (j >= total) return;
+        const uint32_t p = big_list[j];
+        hash_dedup_pair(keys, keys + 2 * MEDIUM_MAX, __ldg(cnt + pair_base + p), __ldg(hit_off + p), line_start, flag);
+    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -799,6 +945,8 @@ int Searcher::init(int device) {
     std::memset(h_small_out_, 0, SMALL_OUT_BYTES);
     PSS_CUDA_TRY(cudaFuncSetAttribute(small_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(SmallSmem)));
+    PSS_CUDA_TRY(cudaFuncSetAttribute(pair_dedup_hash_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(4 * MEDIUM_MAX * sizeof(uint32_t))));
     small_path_ = true;
     if (const char *e = std::getenv("PSS_SMALL_PATH")) small_path_ = std::atoi(e) != 0;
     PSS_TRY(sorter_.init(device_));
@@ -811,9 +959,11 @@ void Searcher::release() {
     cudaSetDevice(device_);
     cudaFree(d_chunks_);
     cudaFree(d_lb_); cudaFree(d_cnt_); cudaFree(d_hit_off_); cudaFree(d_pair_first_);
-    cudaFree(d_entry_off_); cudaFree(d_query_off_);
+    cudaFree(d_entry_off_); cudaFree(d_query_off_); cudaFree(d_heavy_off_); cudaFree(d_start_); cudaFree(d_med_list_); cudaFree(d_big_list_);
     if (h_cnt_) cudaFreeHost(h_cnt_);
     if (h_hit_off_) cudaFreeHost(h_hit_off_);
+    if (h_heavy_off_) cudaFreeHost(h_heavy_off_);
+    if (h_med_list_) cudaFreeHost(h_med_list_);
     cudaFree(d_keys_); cudaFree(d_keys_alt_); cudaFree(d_vals_); cudaFree(d_vals_alt_);
     cudaFree(d_end_); cudaFree(d_flag_); cudaFree(d_tile_sum_); cudaFree(d_scalar_);
     cudaFree(d_out_chunk_); cudaFree(d_out_start_); cudaFree(d_out_end_);
@@ -824,9 +974,9 @@ void Searcher::release() {
     if (stream_) cudaStreamDestroy(stream_);
     sorter_.release();
     d_chunks_ = nullptr;
-    d_lb_ = d_cnt_ = d_hit_off_ = d_pair_first_ = d_entry_off_ = nullptr;
+    d_lb_ = d_cnt_ = d_hit_off_ = d_pair_first_ = d_entry_off_ = d_heavy_off_ = d_start_ = d_med_list_ = d_big_list_ = nullptr;
     d_query_off_ = nullptr;
-    h_cnt_ = h_hit_off_ = nullptr;
+    h_cnt_ = h_hit_off_ = h_heavy_off_ = h_med_list_ = nullptr;
     d_keys_ = d_keys_alt_ = nullptr;
     d_vals_ = d_vals_alt_ = d_end_ = d_flag_ = d_tile_sum_ = d_scalar_ = h_scalar_ = nullptr;
     d_out_chunk_ = nullptr;
@@ -834,7 +984,7 @@ void Searcher::release() {
     h_small_out_ = nullptr;
     for (auto &e : ev_) e = nullptr;
     stream_ = nullptr;
-    pair_cap_ = query_cap_ = hit_cap_ = out_cap_ = 0;
+    pair_cap_ = query_cap_ = hit_cap_ = heavy_cap_ = out_cap_ = 0;
     chunks_.clear();
     device_ = -1;
 }
@@ -886,10 +1036,13 @@ int Searcher::build_newline_index(const uint8_t *d_text, uint32_t n, uint32_t **
 int Searcher::ensure_pairs(int64_t npairs, int64_t nq) {
     if (npairs > pair_cap_) {
         cudaFree(d_lb_); cudaFree(d_cnt_); cudaFree(d_hit_off_); cudaFree(d_pair_first_); cudaFree(d_entry_off_);
+        cudaFree(d_heavy_off_); cudaFree(d_med_list_); cudaFree(d_big_list_);
         if (h_cnt_) cudaFreeHost(h_cnt_);
         if (h_hit_off_) cudaFreeHost(h_hit_off_);
-        d_lb_ = d_cnt_ = d_hit_off_ = d_pair_first_ = d_entry_off_ = nullptr;
-        h_cnt_ = h_hit_off_ = nullptr;
+        if (h_heavy_off_) cudaFreeHost(h_heavy_off_);
+        if (h_med_list_) cudaFreeHost(h_med_list_);
+        d_lb_ = d_cnt_ = d_hit_off_ = d_pair_first_ = d_entry_off_ = d_heavy_off_ = d_med_list_ = d_big_list_ = nullptr;
+        h_cnt_ = h_hit_off_ = h_heavy_off_ = h_med_list_ = nullptr;
         pair_cap_ = 0;
         int64_t cap = std::max<int64_t>(npairs + npairs / 4, 1024);
         PSS_CUDA_TRY(cudaMalloc(&d_lb_, cap * sizeof(uint32_t)));
@@ -897,6 +1050,9 @@ int Searcher::ensure_pairs(int64_t npairs, int64_t nq) {
         PSS_CUDA_TRY(cudaMalloc(&d_hit_off_, (cap + 1) * sizeof(uint32_t)));
         PSS_CUDA_TRY(cudaMalloc(&d_pair_first_, cap * sizeof(uint32_t)));
         PSS_CUDA_TRY(cudaMalloc(&d_entry_off_, (cap + 1) * sizeof(uint32_t)));
+        PSS_CUDA_TRY(cudaMalloc(&d_heavy_off_, (cap + 1) * sizeof(uint32_t)));
+        PSS_CUDA_TRY(cudaMalloc(&d_med_list_, (cap + 1) * sizeof(uint32_t)));
+        PSS_CUDA_TRY(cudaMalloc(&d_big_list_, (cap + 1) * sizeof(uint32_t)));
         pair_cap_ = cap;
     }
     if (nq > query_cap_) {
@@ -912,22 +1068,34 @@ int Searcher::ensure_pairs(int64_t npairs, int64_t nq) {
 
 int Searcher::ensure_hits(int64_t nhits) {
     if (nhits <= hit_cap_) return PSS_OK;
-    cudaFree(d_keys_); cudaFree(d_keys_alt_); cudaFree(d_vals_); cudaFree(d_vals_alt_);
-    cudaFree(d_end_); cudaFree(d_flag_); cudaFree(d_tile_sum_);
-    d_keys_ = d_keys_alt_ = nullptr;
-    d_vals_ = d_vals_alt_ = d_end_ = d_flag_ = d_tile_sum_ = nullptr;
+    cudaFree(d_start_); cudaFree(d_end_); cudaFree(d_flag_); cudaFree(d_tile_sum_);
+    d_start_ = d_end_ = d_flag_ = d_tile_sum_ = nullptr;
     hit_cap_ = 0;
     int64_t cap = std::max<int64_t>(nhits + nhits / 4, 1 << 16);
+    if (cap >= (1ll << 30)) cap = (1ll << 30) - 1;
+    PSS_CUDA_TRY(cudaMalloc(&d_start_, cap * sizeof(uint32_t)));
+    PSS_CUDA_TRY(cudaMalloc(&d_end_, cap * sizeof(uint32_t)));
+    PSS_CUDA_TRY(cudaMalloc(&d_flag_, cap * sizeof(uint32_t)));
+    PSS_CUDA_TRY(cudaMalloc(&d_tile_sum_, (size_t)div_up(cap, CP_TILE) * sizeof(uint32_t)));
+    hit_cap_ = cap;
+    return PSS_OK;
+}
+
+// Sort buffers for the hits of heavy pairs (more than LIGHT_MAX matching suffixes).
+int Searcher::ensure_heavy(int64_t n) {
+    if (n <= heavy_cap_) return PSS_OK;
+    cudaFree(d_keys_); cudaFree(d_keys_alt_); cudaFree(d_vals_); cudaFree(d_vals_alt_);
+    d_keys_ = d_keys_alt_ = nullptr;
+    d_vals_ = d_vals_alt_ = nullptr;
+    heavy_cap_ = 0;
+    int64_t cap = std::max<int64_t>(n + n / 4, 1 << 16);
     if (cap >= (1ll << 30)) cap = (1ll << 30) - 1;
     PSS_CUDA_TRY(cudaMalloc(&d_keys_, cap * sizeof(uint64_t)));
     PSS_CUDA_TRY(cudaMalloc(&d_keys_alt_, cap * sizeof(uint64_t)));
     PSS_CUDA_TRY(cudaMalloc(&d_vals_, cap * sizeof(uint32_t)));
     PSS_CUDA_TRY(cudaMalloc(&d_vals_alt_, cap * sizeof(uint32_t)));
-    PSS_CUDA_TRY(cudaMalloc(&d_end_, cap * sizeof(uint32_t)));
-    PSS_CUDA_TRY(cudaMalloc(&d_flag_, cap * sizeof(uint32_t)));
-    PSS_CUDA_TRY(cudaMalloc(&d_tile_sum_, (size_t)div_up(cap, CP_TILE) * sizeof(uint32_t)));
     PSS_TRY(sorter_.ensure(cap));
-    hit_cap_ = cap;
+    heavy_cap_ = cap;
     return PSS_OK;
 }
 
@@ -1040,25 +1208,29 @@ int Searcher::search(const uint8_t *d_patterns, const int64_t *d_offsets, int32_
         d_chunks_, nc, d_patterns, d_offsets, npairs, d_lb_, d_cnt_);
     PSS_LAUNCH_CHECK();
     PSS_CUDA_TRY(cudaEventRecord(ev_[1], s));
-    hit_offsets_kernel<<<1, SCAN_THREADS, 0, s>>>(d_cnt_, npairs, d_hit_off_,
-                                                   reinterpret_cast<unsigned long long *>(d_scalar_));
+    hit_offsets_kernel<<<1, SCAN_THREADS, 0, s>>>(d_cnt_, npairs, d_hit_off_, d_heavy_off_, d_med_list_,
+                                                   reinterpret_cast<unsigned long long *>(d_scalar_ + 10));
     PSS_LAUNCH_CHECK();
-    PSS_CUDA_TRY(cudaMemcpyAsync(h_scalar_, d_scalar_, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    PSS_CUDA_TRY(cudaMemcpyAsync(h_scalar_ + 10, d_scalar_ + 10, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     PSS_CUDA_TRY(cudaStreamSynchronize(s));
-    const uint64_t total_hits = (uint64_t)h_scalar_[0] | ((uint64_t)h_scalar_[1] << 32);
+    const uint64_t total_hits  = (uint64_t)h_scalar_[10] | ((uint64_t)h_scalar_[11] << 32);
+    const uint64_t total_heavy = (uint64_t)h_scalar_[12] | ((uint64_t)h_scalar_[13] << 32);
+    const uint32_t total_medium = h_scalar_[14];
     out->n_hits = (int64_t)total_hits;
 
     // ---- sub-batches of pairs whose hits fit the workspace (normally: one) --------------------
     constexpr int64_t HIT_BUDGET = 1ll << 27;
-    struct Sub { uint32_t a, np; uint32_t nh; uint32_t hit_base; bool device_offsets; };
+    struct Sub { uint32_t a, np; uint32_t nh; uint32_t n_heavy, n_medium; bool device_offsets; };
     std::vector<Sub> subs;
     if (total_hits <= (uint64_t)HIT_BUDGET) {
-        if (total_hits) subs.push_back({0u, npairs, (uint32_t)total_hits, 0u, true});
+        if (total_hits) subs.push_back({0u, npairs, (uint32_t)total_hits, (uint32_t)total_heavy, total_medium, true});
     } else {
         // oversized batch: the per-pair counts come to the host once and are cut there
         if (!h_cnt_) {
             PSS_CUDA_TRY(cudaMallocHost(&h_cnt_, (size_t)pair_cap_ * sizeof(uint32_t)));
             PSS_CUDA_TRY(cudaMallocHost(&h_hit_off_, ((size_t)pair_cap_ + 1) * sizeof(uint32_t)));
+            PSS_CUDA_TRY(cudaMallocHost(&h_heavy_off_, ((size_t)pair_cap_ + 1) * sizeof(uint32_t)));
+            PSS_CUDA_TRY(cudaMallocHost(&h_med_list_, ((size_t)pair_cap_ + 1) * sizeof(uint32_t)));
         }
         PSS_CUDA_TRY(cudaMemcpyAsync(h_cnt_, d_cnt_, (size_t)npairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         PSS_CUDA_TRY(cudaStreamSynchronize(s));
@@ -1068,7 +1240,7 @@ int Searcher::search(const uint8_t *d_patterns, const int64_t *d_offsets, int32_
             uint32_t b = a;
             while (b < npairs && (H == 0 || H + h_cnt_[b] <= HIT_BUDGET)) H += h_cnt_[b++];
             if (H >= (1ll << 30)) return fail(PSS_ERR_ARG, "a single (query, chunk) pair has >= 2^30 hits");
-            if (H) subs.push_back({a, b - a, (uint32_t)H, 0u, false});
+            if (H) subs.push_back({a, b - a, (uint32_t)H, 0u, 0u, false});
             a = b;
         }
     }
@@ -1081,17 +1253,34 @@ int Searcher::search(const uint8_t *d_patterns, const int64_t *d_offsets, int32_
         PSS_TRY(ensure_hits(sb.nh));
         if ((int64_t)entries + sb.nh >= (1ll << 32)) return fail(PSS_ERR_ARG, "more than 2^32 entries in one batch");
         if (!defer) PSS_TRY(ensure_out((int64_t)entries + sb.nh, s));   // entries <= matching suffixes: no count needed up front
-        const uint32_t *hit_off = d_hit_off_ + sb.a;
-        uint32_t hit_base = 0;
+        const uint32_t *hit_off = d_hit_off_ + sb.a, *heavy_off = d_heavy_off_ + sb.a;
+        const uint32_t hit_base = 0;                         // offsets are relative to the sub-batch
+        uint32_t n_heavy = sb.n_heavy, n_medium = sb.n_medium;
+        const uint32_t *med_list = d_med_list_ + sb.a;
         if (sb.device_offsets) {
-            hit_base = 0;                                    // a == 0: offsets are already relative
+            med_list = d_med_list_;
         } else {
-            uint32_t run = 0;
-            for (uint32_t p = 0; p < sb.np; ++p) { h_hit_off_[p] = run; run += h_cnt_[sb.a + p]; }
+            uint32_t run = 0, hrun = 0, mrun = 0;
+            for (uint32_t p = 0; p < sb.np; ++p) {
+                const uint32_t c = h_cnt_[sb.a + p];
+                h_hit_off_[p] = run;
+                h_heavy_off_[p] = hrun;
+                run += c;
+                if (c > MEDIUM_MAX) hrun += c;
+                else if (c > LIGHT_MAX) h_med_list_[mrun++] = p;
+            }
             h_hit_off_[sb.np] = run;
+            n_heavy = hrun;
+            n_medium = mrun;
             PSS_CUDA_TRY(cudaMemcpyAsync(d_hit_off_ + sb.a, h_hit_off_, ((size_t)sb.np + 1) * sizeof(uint32_t),
                                          cudaMemcpyHostToDevice, s));
+            PSS_CUDA_TRY(cudaMemcpyAsync(d_heavy_off_ + sb.a, h_heavy_off_, (size_t)sb.np * sizeof(uint32_t),
+                                         cudaMemcpyHostToDevice, s));
+            if (mrun)
+                PSS_CUDA_TRY(cudaMemcpyAsync(d_med_list_ + sb.a, h_med_list_, (size_t)mrun * sizeof(uint32_t),
+                                             cudaMemcpyHostToDevice, s));
         }
+        PSS_TRY(ensure_heavy(n_heavy));
         // pairs skipped between sub-batches (no hits) get their entry offset here
         if (sb.a > next_pair) {
             std::vector<uint32_t> fill(sb.a - next_pair, entries);
@@ -1100,21 +1289,37 @@ int Searcher::search(const uint8_t *d_patterns, const int64_t *d_offsets, int32_
             PSS_CUDA_TRY(cudaStreamSynchronize(s));
         }
         const uint32_t nh = sb.nh;
+        const uint32_t tiles = (uint32_t)div_up(nh, CP_TILE);
+        PSS_CUDA_TRY(cudaMemsetAsync(d_flag_, 0, (size_t)nh * sizeof(uint32_t), s));
         PSS_CUDA_TRY(cudaEventRecord(ev_[2], s));
-        extract_kernel<<<(unsigned)div_up(nh, 256), 256, 0, s>>>(d_chunks_, nc, sb.a, sb.np, hit_off, hit_base, d_lb_, nh,
-                                                                sbits, d_keys_, d_end_);
+        extract_kernel<<<(unsigned)div_up(nh, 256), 256, 0, s>>>(d_chunks_, nc, sb.a, sb.np, hit_off, heavy_off, d_lb_, d_cnt_,
+                                                                nh, sbits, d_start_, d_end_, d_keys_, d_vals_);
         PSS_LAUNCH_CHECK();
         PSS_CUDA_TRY(cudaEventRecord(ev_[3], s));
 
-        bool in_alt = false;
-        const int end_bit = sbits + std::max(1, bit_width_u64((uint64_t)sb.np - 1));
-        PSS_TRY(sorter_.sort_async(d_keys_, d_keys_alt_, d_vals_, d_vals_alt_, nh, 0, end_bit, /*iota=*/true, s, &in_alt));
-        const uint64_t *k_sorted = in_alt ? d_keys_alt_ : d_keys_;
-        const uint32_t *v_sorted = in_alt ? d_vals_alt_ : d_vals_;
-        const uint32_t tiles = (uint32_t)div_up(nh, CP_TILE);
-        PSS_CUDA_TRY(cudaMemsetAsync(d_flag_, 0, (size_t)nh * sizeof(uint32_t), s));
-        mark_kernel<<<(unsigned)div_up(nh, 256), 256, 0, s>>>(k_sorted, v_sorted, nh, sbits, d_flag_);
+        // dedup: light pairs by one warp each; heavy pairs through the stable sort of
+        // (pair, entry start) with the hit index as value
+        pair_dedup_kernel<<<(unsigned)div_up(sb.np, PD_WARPS), PD_WARPS * 32, 0, s>>>(hit_off, d_cnt_, sb.a, sb.np, d_start_, d_flag_);
         PSS_LAUNCH_CHECK();
+        if (n_medium) {
+            PSS_CUDA_TRY(cudaMemsetAsync(d_scalar_ + 5, 0, 2 * sizeof(uint32_t), s));   // big-pair count, cursor
+            pair_dedup_hash_kernel<<<n_medium, PH_THREADS, 4 * PH_SMALL_MAX * sizeof(uint32_t), s>>>(
+                med_list, hit_off, d_cnt_, sb.a, d_start_, d_flag_, d_big_list_, d_scalar_ + 5);
+            PSS_LAUNCH_CHECK();
+            pair_dedup_hash_big_kernel<<<(unsigned)std::min<uint32_t>(n_medium, (uint32_t)sorter_.num_sms()), PH_THREADS,
+                                         4 * MEDIUM_MAX * sizeof(uint32_t), s>>>(d_big_list_, d_scalar_ + 5, d_scalar_ + 6, hit_off,
+                                                                                 d_cnt_, sb.a, d_start_, d_flag_);
+            PSS_LAUNCH_CHECK();
+        }
+        if (n_heavy) {
+            bool in_alt = false;
+            const int end_bit = sbits + std::max(1, bit_width_u64((uint64_t)sb.np - 1));
+            PSS_TRY(sorter_.sort_async(d_keys_, d_keys_alt_, d_vals_, d_vals_alt_, n_heavy, 0, end_bit, /*iota=*/false, s, &in_alt));
+            const uint64_t *k_sorted = in_alt ? d_keys_alt_ : d_keys_;
+            const uint32_t *v_sorted = in_alt ? d_vals_alt_ : d_vals_;
+            mark_kernel<<<(unsigned)div_up(n_heavy, 256), 256, 0, s>>>(k_sorted, v_sorted, n_heavy, sbits, d_flag_);
+            PSS_LAUNCH_CHECK();
+        }
         flag_reduce_kernel<<<tiles, CP_THREADS, 0, s>>>(d_flag_, nh, d_tile_sum_);
         PSS_LAUNCH_CHECK();
         tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(d_tile_sum_, tiles, d_scalar_ + 2);

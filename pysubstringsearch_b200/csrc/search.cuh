@@ -12,9 +12,12 @@
 //            SCAN_LIMIT bytes one binary search in the chunk's newline side index
 //            (sorted '\n' offsets, derived on the device when the chunk is loaded), so the
 //            cost per hit is bounded whatever the line length
-//   dedup    stable onesweep sort of (pair id, entry start) → the first record of every
-//            run is the entry's first hit in SA order (lib.rs:262,274 uses a hash set);
-//            survivors are compacted back in SA order, which is the reference's order
+//   dedup    the first hit in SA order stands for an entry (lib.rs:262,274 uses a hash set).
+//            Three tiers by the pair's number of matching suffixes: up to 256 — one warp,
+//            all-pairs compare in shared memory; up to 8192 — one CTA, a hash set of entry
+//            starts in shared memory that keeps the smallest hit index; above — a stable
+//            onesweep sort of (pair id, entry start) whose run heads are the first hits.
+//            Survivors are compacted back in SA order, which is the reference's order
 //
 // Counts, offsets and the per-(query, chunk) entry offsets stay on the device; the host
 // reads two scalars per batch (matching suffixes, entries).  A batch of a few pairs
@@ -113,6 +116,7 @@ public:
 private:
     int ensure_pairs(int64_t npairs, int64_t nq);
     int ensure_hits(int64_t nhits);
+    int ensure_heavy(int64_t n);
     int ensure_out(int64_t entries, cudaStream_t s);
 
     int          device_ = -1;
@@ -123,21 +127,24 @@ private:
 
     int64_t   pair_cap_ = 0, query_cap_ = 0;
     uint32_t *d_lb_ = nullptr, *d_cnt_ = nullptr, *d_hit_off_ = nullptr, *d_pair_first_ = nullptr;
-    uint32_t *d_entry_off_ = nullptr;
+    uint32_t *d_entry_off_ = nullptr, *d_heavy_off_ = nullptr, *d_med_list_ = nullptr, *d_big_list_ = nullptr;
     int64_t  *d_query_off_ = nullptr;
-    uint32_t *h_cnt_ = nullptr, *h_hit_off_ = nullptr;   // pinned; only the oversized-batch path uses them
+    // pinned; only the oversized-batch path uses them
+    uint32_t *h_cnt_ = nullptr, *h_hit_off_ = nullptr, *h_heavy_off_ = nullptr, *h_med_list_ = nullptr;
 
-    int64_t   hit_cap_ = 0;
+    int64_t   hit_cap_ = 0;                              // per matching suffix: entry start / end, keep flag
+    uint32_t *d_start_ = nullptr, *d_end_ = nullptr, *d_flag_ = nullptr, *d_tile_sum_ = nullptr;
+    int64_t   heavy_cap_ = 0;                            // sort buffers for the hits of heavy pairs only
     uint64_t *d_keys_ = nullptr, *d_keys_alt_ = nullptr;
     uint32_t *d_vals_ = nullptr, *d_vals_alt_ = nullptr;
-    uint32_t *d_end_ = nullptr, *d_flag_ = nullptr, *d_tile_sum_ = nullptr;
 
     int64_t   out_cap_ = 0;
     int32_t  *d_out_chunk_ = nullptr;
     uint32_t *d_out_start_ = nullptr, *d_out_end_ = nullptr;
 
-    // scalars: [0..1] total matching suffixes (u64), [2] entries of the current sub-batch,
-    // [3] small-path ticket
+    // scalars: [2] entries of the current sub-batch, [3] small-path ticket, [4] newline count,
+    // [5] pairs queued for the large hash tables, [6] their cursor,
+    // [10..11] total matching suffixes (u64), [12..13] those of heavy pairs (u64), [14..15] medium pairs (u64)
     uint32_t *d_scalar_ = nullptr, *h_scalar_ = nullptr;
     unsigned char *h_small_out_ = nullptr;   // mapped pinned result block of the small path
     uint32_t  small_seq_ = 0;
