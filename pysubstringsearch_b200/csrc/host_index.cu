@@ -347,6 +347,7 @@ pss_reader::~pss_reader() {
     for (auto &c : chunks) {
         if (!c.borrowed) { cudaFree(c.d_text); cudaFree(c.d_sa); }
         cudaFree(c.d_nl);
+        cudaFree(c.d_bucket);
     }
     cudaFree(d_pat);
     if (ev0) cudaEventDestroy(ev0);
@@ -393,8 +394,9 @@ static int reader_finish_open(pss_reader *r) {
         ChunkHost &c = r->chunks[k];
         if (!c.owned || c.n == 0) continue;
         PSS_TRY(r->searcher.build_newline_index(c.d_text, c.n, &c.d_nl, &c.n_lines));
+        PSS_TRY(r->searcher.build_prefix_buckets(c.d_text, c.d_sa, c.n, &c.d_bucket));
         DeviceChunk dc = {};
-        dc.text = c.d_text; dc.sa = c.d_sa; dc.nl = c.d_nl; dc.n = c.n; dc.n_lines = c.n_lines;
+        dc.text = c.d_text; dc.sa = c.d_sa; dc.nl = c.d_nl; dc.bucket = c.d_bucket; dc.n = c.n; dc.n_lines = c.n_lines;
         dc.global_id = (int32_t)k;
         dchunks.push_back(dc);
     }

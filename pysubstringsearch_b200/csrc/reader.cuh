@@ -125,6 +125,7 @@ struct ChunkHost {
     uint8_t  *d_text = nullptr;
     int32_t  *d_sa   = nullptr;
     uint32_t *d_nl   = nullptr;            // newline side index (always ours)
+    uint32_t *d_bucket = nullptr;          // 2-byte prefix table over the SA (always ours)
     uint32_t  n_lines = 0;
 };
 

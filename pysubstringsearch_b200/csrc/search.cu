@@ -45,11 +45,19 @@ __device__ __forceinline__ int cmp_suffix(const uint8_t *__restrict__ text, uint
 // Range of SA slots whose suffixes start with P, found by the whole warp: lower bound, then
 // upper bound starting from it (the reference runs the same two searches, lib.rs:212-252).
 __device__ __forceinline__ void warp_bounds(const uint8_t *__restrict__ text, const int32_t *__restrict__ sa, uint32_t n,
+                                            const uint32_t *__restrict__ bucket,
                                             const uint8_t *__restrict__ P, uint32_t m, uint32_t lane,
                                             uint32_t *lb_out, uint32_t *cnt_out) {
     const uint32_t pc0 = lane < m ? (uint32_t)__ldg(P + lane) : 0u;
+    // every match lies inside the bucket of the pattern's first two bytes
+    uint32_t lo = 0, hi_all = n;
+    if (bucket != nullptr && m >= 2) {
+        const uint32_t key = (__shfl_sync(0xffffffffu, pc0, 0) << 8) | __shfl_sync(0xffffffffu, pc0, 1);
+        lo     = min(__ldg(bucket + key), n);                 // clamped: a corrupt index must not send probes out of range
+        hi_all = min(max(__ldg(bucket + key + 1), lo), n);
+    }
     // smallest slot whose suffix is >= P (as a prefix comparison)
-    uint32_t lo = 0, hi = n;
+    uint32_t hi = hi_all;
     while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
         if (cmp_suffix(text, n, (uint32_t)__ldg(sa + mid), P, m, pc0, lane) < 0) lo = mid + 1;
@@ -57,7 +65,7 @@ __device__ __forceinline__ void warp_bounds(const uint8_t *__restrict__ text, co
     }
     const uint32_t lb = lo;
     // smallest slot past lb whose suffix is > P and does not start with it
-    hi = n;
+    hi = hi_all;
     while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
         if (cmp_suffix(text, n, (uint32_t)__ldg(sa + mid), P, m, pc0, lane) <= 0) lo = mid + 1;
@@ -79,7 +87,7 @@ bounds_kernel(const DeviceChunk *__restrict__ chunks, int nc, const uint8_t *__r
     // a malformed offsets array (device callers) must not turn into a wild pattern length
     const int64_t o0 = pat_off[q], o1 = pat_off[q + 1];
     const uint32_t m = o1 > o0 ? (uint32_t)min(o1 - o0, (int64_t)0x7FFFFFFF) : 0u;
-    warp_bounds(chunks[c].text, chunks[c].sa, chunks[c].n, patterns + o0, m, lane, &lb, &cnt);
+    warp_bounds(chunks[c].text, chunks[c].sa, chunks[c].n, chunks[c].bucket, patterns + o0, m, lane, &lb, &cnt);
     if (lane == 0) {
         lb_out[pair]  = lb;
         cnt_out[pair] = cnt;
@@ -256,6 +264,35 @@ newline_fill_kernel(const uint8_t *__restrict__ text, uint32_t n, const uint32_t
         nl[o++] = at + b;
         m &= m - 1;
     }
+}
+
+// ------------------------------------------------------------------------------------
+// 2-byte prefix table: bucket[a << 8 | b] = first SA slot whose suffix starts with a, b.
+// Boundaries are where the prefix changes along the suffix array; the thread at a boundary
+// fills every table entry between the two prefixes.  A one-byte suffix "c" (the text's last
+// position) takes the key (c, 0): it sorts directly before every "c\0..." suffix, so buckets stay
+// contiguous and ordered (a bucket may hold it without matching — the searches skip it).
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t prefix_key(const uint8_t *__restrict__ text, uint32_t n, uint32_t pos) {
+    const uint32_t a = __ldg(text + pos);
+    const uint32_t b = pos + 1 < n ? (uint32_t)__ldg(text + pos + 1) : 0u;
+    return (a << 8) | b;
+}
+
+__global__ void __launch_bounds__(256)
+prefix_bucket_kernel(const uint8_t *__restrict__ text, const int32_t *__restrict__ sa, uint32_t n,
+                     uint32_t *__restrict__ bucket) {
+    const uint32_t k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t cur = prefix_key(text, n, (uint32_t)__ldg(sa + k));
+    if (k == 0) {
+        for (uint32_t j = 0; j <= cur; ++j) bucket[j] = 0;
+    } else {
+        const uint32_t prev = prefix_key(text, n, (uint32_t)__ldg(sa + k - 1));
+        for (uint32_t j = prev + 1; j <= cur; ++j) bucket[j] = k;       // empty when prev == cur
+    }
+    if (k == n - 1)
+        for (uint32_t j = cur + 1; j <= 65536u; ++j) bucket[j] = n;
 }
 
 // ------------------------------------------------------------------------------------
@@ -713,6 +750,11 @@ small_search_kernel(const DeviceChunk *__restrict__ chunks, int nc, const __grid
         const uint32_t which = tid / T;        // 0: lower bound (first slot with cmp >= 0), 1: upper (first with cmp > 0)
         const uint32_t t     = tid % T;
         uint32_t lo = 0, hi = n;               // the answer lies in [lo, hi]
+        if (chunks[c].bucket != nullptr && m >= 2) {          // inside the bucket of the first two pattern bytes
+            const uint32_t key = ((uint32_t)s.pat[0] << 8) | s.pat[1];
+            lo = min(__ldg(chunks[c].bucket + key), n);
+            hi = min(max(__ldg(chunks[c].bucket + key + 1), lo), n);
+        }
         while (true) {                         // both halves iterate in lockstep (block barriers)
             const uint32_t R = hi - lo;
             bool below = false;                // predicate "boundary is past my pivot"
@@ -1030,6 +1072,25 @@ int Searcher::build_newline_index(const uint8_t *d_text, uint32_t n, uint32_t **
     }
     *d_nl = nl;
     *n_lines = L;
+    return PSS_OK;
+}
+
+int Searcher::build_prefix_buckets(const uint8_t *d_text, const int32_t *d_sa, uint32_t n, uint32_t **d_bucket) {
+    *d_bucket = nullptr;
+    if (n == 0) return PSS_OK;
+    PSS_CUDA_TRY(cudaSetDevice(device_));
+    uint32_t *b = nullptr;
+    PSS_CUDA_TRY(cudaMalloc(&b, 65537 * sizeof(uint32_t)));
+    cudaMemsetAsync(b, 0, 65537 * sizeof(uint32_t), stream_);
+    prefix_bucket_kernel<<<(unsigned)div_up(n, 256), 256, 0, stream_>>>(d_text, d_sa, n, b);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
+    if (e != cudaSuccess) {
+        cudaFree(b);
+        return fail(PSS_ERR_CUDA, std::string("prefix buckets: ") + cudaGetErrorString(e));
+    }
+    *d_bucket = b;
     return PSS_OK;
 }
 

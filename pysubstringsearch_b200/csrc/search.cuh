@@ -37,6 +37,7 @@ struct DeviceChunk {
     const uint8_t  *text;      // device, 16 readable zero bytes past n
     const int32_t  *sa;        // device
     const uint32_t *nl;        // device: sorted offsets of every '\n' (may be null: unbounded scans)
+    const uint32_t *bucket;    // device: [65537] first SA slot of every 2-byte prefix (may be null: full-range search)
     uint32_t        n;
     uint32_t        n_lines;   // entries of nl
     int32_t         global_id;
@@ -89,6 +90,12 @@ public:
     // Builds the newline side index of a chunk already resident on this device: *d_nl
     // (cudaMalloc'ed here, owned by the caller) and *n_lines.
     int build_newline_index(const uint8_t *d_text, uint32_t n, uint32_t **d_nl, uint32_t *n_lines);
+
+    // Builds the 2-byte prefix table of a resident chunk: (*d_bucket)[a << 8 | b] = first SA slot
+    // whose suffix starts with bytes a, b (entry 65536 = n).  A pattern of two or more bytes is
+    // then searched inside its bucket only: ~10 of the 29 probe levels of a 2^29-byte chunk
+    // disappear from both binary searches.  cudaMalloc'ed here, owned by the caller.
+    int build_prefix_buckets(const uint8_t *d_text, const int32_t *d_sa, uint32_t n, uint32_t **d_bucket);
 
     // d_patterns / d_offsets: device.  Synchronises `stream` before returning (the counts
     // in *out are host values).
