@@ -351,7 +351,12 @@ int32_t pss_comm_destroy(pss_comm *c);
  * searches its own chunks; rank 0 receives exactly the tuples found (no padding), places
  * them in the single-process order (query, ascending chunk id, SA order) and returns them
  * in *out; on other ranks *out is an empty result.  One exchange step per batch:
- * broadcast(patterns) → local search → gather-v(entry offsets, tuples) → placement.
+ * broadcast(patterns) → local search → all-gather(per-pair entry offsets) → every rank's
+ * compaction kernel stores its tuples at their final positions in rank 0's result arrays
+ * over NVLink peer memory (CUDA IPC; where peers cannot be mapped, or with
+ * PSS_DIST_FUSED=0 on every rank: NCCL gather-v of exact counts + a placement kernel).
+ * As with any collective, a rank that fails (or does not call) leaves the others waiting:
+ * treat an error on one rank as fatal for the job.
  */
 int32_t pss_reader_search_batch_dist(pss_reader *r, pss_comm *c, const uint8_t *patterns,
                                      const int64_t *offsets, int32_t nq, pss_result **out);

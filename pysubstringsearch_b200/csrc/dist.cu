@@ -506,6 +506,7 @@ int fused_grow(pss_comm *c, cudaStream_t s, int64_t entries, bool *ok) {
 
 int fused_setup(pss_comm *c, cudaStream_t s) {
     c->fused = 0;
+    if (c->world > 16) return PSS_OK;           // the count words of the staging block hold 16 ranks: one node
     if (const char *e = std::getenv("PSS_DIST_FUSED"))
         if (std::atoi(e) == 0) return PSS_OK;
     PSS_CUDA_TRY(cudaMalloc(&c->d_small, 64 * sizeof(uint32_t)));
@@ -570,9 +571,8 @@ int dist_search_fused(pss_reader *r, pss_comm *c, int32_t nq, int64_t total, Dis
     PSS_CUDA_TRY(cudaMemcpyAsync(d_desc, h_desc, need_h, cudaMemcpyHostToDevice, s));
     dist_counts_kernel<<<1, 32, 0, s>>>(d_desc, G, c->d_small + 44);
     PSS_LAUNCH_CHECK();
-    PSS_TRY(copy_words(c->h_small + 44, c->d_small + 44, G <= 16 ? G : 16, s));
+    PSS_TRY(copy_words(c->h_small + 44, c->d_small + 44, G, s));
     PSS_CUDA_TRY(cudaStreamSynchronize(s));      // the one host read of the exchange: entries per rank
-    if (G > 16) return fail(PSS_ERR_ARG, "fused exchange supports up to 16 ranks");
     int64_t total_entries = 0;
     for (int q = 0; q < G; ++q) total_entries += c->h_small[44 + q];
     if (c->h_small[44 + me] != (uint32_t)so.n_entries) return fail(PSS_ERR_CUDA, "distributed search: inconsistent local entry count");
