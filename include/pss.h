@@ -84,10 +84,10 @@ int32_t pss_libsais(const uint8_t *T, int32_t *SA, int32_t n, int32_t fs, int32_
  *   pss_sa_build_wait(h, SA)               blocks until the build is done, copies SA[0..n)
  *                                          to host memory (pinned or pageable), frees h
  *
- * Each device runs its builds in begin order on one worker thread and keeps two
- * (text, SA) slots in HBM: the device→host copy done by wait(k) overlaps H2D + build of
- * k+1.  Wait for the handles of one device in begin order, with at most two of them
- * begun-but-not-waited ahead of the one being waited for.  Same return codes as pss_libsais.
+ * Each device runs its builds in begin order on one worker thread and keeps three
+ * (text, SA) slots in HBM: while chunk k is built, the text of k+1 is uploaded and the
+ * device→host copy done by wait(k-1) runs.  Any number of builds may be queued; wait for
+ * the handles of one device in begin order.  Same return codes as pss_libsais.
  */
 typedef struct pss_sa_build pss_sa_build;
 int32_t pss_sa_build_begin(int32_t device, const uint8_t *T, int32_t n, pss_sa_build **out);

@@ -355,6 +355,8 @@ const PassConfig kPassConfigs[] = {
     PSS_PASS_CONFIG(512, 8, 2),    // 2: 4096-record tiles, 2 CTAs/SM
     PSS_PASS_CONFIG(384, 16, 2),   // 3: 6144-record tiles, 2 CTAs/SM
     PSS_PASS_CONFIG(256, 24, 2),   // 4: 6144-record tiles, 2 CTAs/SM
+    PSS_PASS_CONFIG(256, 14, 4),   // 5: 3584-record tiles, 4 CTAs/SM at 64 registers (3.09 TB/s: smaller tiles lose more
+    PSS_PASS_CONFIG(256, 12, 4),   // 6: 3072-record tiles, 4 CTAs/SM (3.22 TB/s)       than the occupancy gains)
 };
 constexpr int kNumPassConfigs = (int)(sizeof(kPassConfigs) / sizeof(kPassConfigs[0]));
 
