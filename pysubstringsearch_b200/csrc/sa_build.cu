@@ -546,6 +546,7 @@ int SaBuilder::init(int device, int64_t max_n) {
         cudaGetLastError();
     }
     if (const char *e = std::getenv("PSS_L2_HINTS")) l2_hints_ = std::atoi(e);
+    if (const char *e = std::getenv("PSS_GATHER_CTAS")) gather_ctas_ = std::max(1, std::atoi(e));
     PSS_CUDA_TRY(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     PSS_CUDA_TRY(cudaEventCreate(&ev_begin_));
     PSS_CUDA_TRY(cudaEventCreate(&ev_end_));
@@ -754,7 +755,7 @@ int SaBuilder::build_device(const uint8_t *d_text, int32_t n, int32_t *d_sa, cud
         uint32_t *v_alt = (v_in == vals_a_) ? vals_b_ : vals_a_;
         PSS_TRY(sorter_.hist_reset(s));
         {
-            const int grid = (int)std::min<int64_t>(div_up(n_active, 256 * 4), (int64_t)sorter_.num_sms() * 8);
+            const int grid = (int)std::min<int64_t>(div_up(n_active, 256 * 4), (int64_t)sorter_.num_sms() * gather_ctas_);
             gather_kernel<<<grid, 256, 0, s>>>(v_in, grp_, isa_, un, (uint32_t)std::min<uint64_t>(h, un), rbits, n_active,
                                                keys_a_, hist_layout(0, rbits + gbits), sorter_.d_hist(), l2_hints_);
             PSS_LAUNCH_CHECK();

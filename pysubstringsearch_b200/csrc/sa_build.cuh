@@ -92,6 +92,11 @@ private:
     cudaEvent_t  ev_begin_ = nullptr, ev_end_ = nullptr;
     HostStager   stager_;                              // pinned bounce slices for pageable callers
     bool         profiling_ = false;
+    // CTAs per SM of the rank gather (PSS_GATHER_CTAS).  More records in flight than ~600 k and
+    // the 128-byte fills of the random ISA reads evict the index window from L2 before it is
+    // reused: at 8 CTAs/SM the round-1 gather of a 2^29-byte chunk read 38.7 GB from DRAM in
+    // 7.35 ms, at 4 it reads 12.3 GB in 4.60 ms, at 2 the ideal 5.4 GB but latency-bound (6.65 ms).
+    int          gather_ctas_ = 4;
     int          l2_hints_ = 1;           // PSS_L2_HINTS=0 disables the evict_last / evict_first cache hints
     pss_build_stats stats_ = {};
     std::vector<pss_pass_stat> pass_stats_;
