@@ -266,6 +266,23 @@ newline_fill_kernel(const uint8_t *__restrict__ text, uint32_t n, const uint32_t
     }
 }
 
+// Line directory: dir[j] = number of '\n' at text positions < j * LINE_BLOCK (j = 0 .. ceil(n / LINE_BLOCK)),
+// i.e. where the newlines of text block j start inside the sorted offset list.  One binary search
+// per block at open; extraction then needs no search over the whole list (entry_bounds).
+__global__ void __launch_bounds__(256)
+line_directory_kernel(const uint32_t *__restrict__ nl, uint32_t n_lines, uint32_t n_dir, uint32_t *__restrict__ dir) {
+    const uint32_t j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= n_dir) return;
+    const uint64_t at = (uint64_t)j * LINE_BLOCK;
+    uint32_t lo = 0, hi = n_lines;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if ((uint64_t)__ldg(nl + mid) < at) lo = mid + 1;
+        else hi = mid;
+    }
+    dir[j] = lo;
+}
+
 // ------------------------------------------------------------------------------------
 // 2-byte prefix table: bucket[a << 8 | b] = first SA slot whose suffix starts with a, b.
 // Boundaries are where the prefix changes along the suffix array; the thread at a boundary
@@ -317,7 +334,62 @@ constexpr uint32_t SCAN_LIMIT = 64;   // bytes scanned each way before the newli
 
 // Entry around text position pos: *b = 1 + last '\n' strictly before pos (none → 0,
 // lib.rs:270-273), *e = first '\n' at or after pos (none → n - 1, lib.rs:266-269).
+//
+// With the line directory (every Reader builds it at open) no text is read at all: the block
+// of pos gives the first newline offset of that block inside the sorted list (one random
+// sector), and the nine offsets nl[lo - 1 .. lo + 8) loaded together (one or two more
+// sectors, all in flight at once) hold both neighbours of pos unless the 256-byte block has
+// more than eight newlines before pos.  Two dependent DRAM round trips per matching suffix,
+// whatever the line length; the text scan it replaces walked 4 bytes per dependent load, crossed
+// two or three sectors per 45-byte line and fell back to a 24-probe search over the whole list
+// for every line end further than 64 bytes away (a quarter of the hits each way).
+__device__ __forceinline__ void entry_bounds_dir(const DeviceChunk &ch, uint32_t pos, uint32_t *b_out, uint32_t *e_out) {
+    const uint32_t *__restrict__ nl = ch.nl;
+    const uint32_t L = ch.n_lines;
+    if (L == 0) {                                            // a chunk without any '\n'
+        *b_out = 0;
+        *e_out = ch.n - 1;
+        return;
+    }
+    const uint32_t blk = pos / LINE_BLOCK;
+    const uint32_t lo = __ldg(ch.dir + blk);
+    // unconditional loads at clamped indices: all nine are in flight together (a load guarded by
+    // `idx < L` compiles to nine dependent branch-load-compare steps)
+    uint32_t x[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) x[j] = __ldg(nl + min(lo + (uint32_t)j - 1u, L - 1u));
+    uint32_t e = 0xFFFFFFFFu, b = 0;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        const uint32_t idx = lo + (uint32_t)j - 1u;          // lo == 0, j == 0 wraps to 0xFFFFFFFF: out of range
+        const uint32_t v   = idx < L ? x[j] : 0xFFFFFFFFu;
+        b = v < pos ? v + 1 : b;                             // ascending: the last one below pos stands
+        e = v < pos ? e : min(e, v);
+    }
+    if (e == 0xFFFFFFFFu) {
+        if (lo + 8 >= L) {
+            e = ch.n - 1;                                    // no '\n' at or after pos (lib.rs:266-269: None -> len - 1)
+        } else {
+            // more than eight newlines of this block lie before pos: search the rest of the block
+            uint32_t l = lo + 8, h = __ldg(ch.dir + blk + 1);
+            while (l < h) {
+                const uint32_t mid = l + ((h - l) >> 1);
+                if (__ldg(nl + mid) < pos) l = mid + 1;
+                else h = mid;
+            }
+            e = l < L ? __ldg(nl + l) : ch.n - 1;
+            b = __ldg(nl + l - 1) + 1;                       // l >= lo + 8 >= 1
+        }
+    }
+    *b_out = b;
+    *e_out = e;
+}
+
 __device__ __forceinline__ void entry_bounds(const DeviceChunk &ch, uint32_t pos, uint32_t *b_out, uint32_t *e_out) {
+    if (ch.dir != nullptr) {
+        entry_bounds_dir(ch, pos, b_out, e_out);
+        return;
+    }
     const uint8_t *__restrict__ text = ch.text;
     const uint32_t n = ch.n;
     const bool bounded = ch.nl != nullptr;
@@ -1072,6 +1144,25 @@ int Searcher::build_newline_index(const uint8_t *d_text, uint32_t n, uint32_t **
     }
     *d_nl = nl;
     *n_lines = L;
+    return PSS_OK;
+}
+
+int Searcher::build_line_directory(const uint32_t *d_nl, uint32_t n_lines, uint32_t n, uint32_t **d_dir) {
+    *d_dir = nullptr;
+    if (n == 0 || !d_nl) return PSS_OK;
+    PSS_CUDA_TRY(cudaSetDevice(device_));
+    const uint32_t n_dir = (uint32_t)div_up(n, LINE_BLOCK) + 1;   // dir[ceil(n / LINE_BLOCK)] = n_lines
+    uint32_t *dir = nullptr;
+    PSS_CUDA_TRY(cudaMalloc(&dir, (size_t)n_dir * sizeof(uint32_t)));
+    line_directory_kernel<<<(unsigned)div_up(n_dir, 256), 256, 0, stream_>>>(d_nl, n_lines, n_dir, dir);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
+    if (e != cudaSuccess) {
+        cudaFree(dir);
+        return fail(PSS_ERR_CUDA, std::string("line directory: ") + cudaGetErrorString(e));
+    }
+    *d_dir = dir;
     return PSS_OK;
 }
 

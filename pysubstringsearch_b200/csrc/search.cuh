@@ -38,11 +38,16 @@ struct DeviceChunk {
     const int32_t  *sa;        // device
     const uint32_t *nl;        // device: sorted offsets of every '\n' (may be null: unbounded scans)
     const uint32_t *bucket;    // device: [65537] first SA slot of every 2-byte prefix (may be null: full-range search)
+    const uint32_t *dir;       // device: [ceil(n / LINE_BLOCK) + 1] newlines before every text block (may be null: text scans)
     uint32_t        n;
     uint32_t        n_lines;   // entries of nl
     int32_t         global_id;
     int32_t         reserved;
 };
+
+// Text bytes per entry of the line directory: 256 → 1/64 of the text's size, ~6 newlines of a
+// 45-byte-line corpus per block, so the nine offsets extraction loads almost always decide.
+constexpr uint32_t LINE_BLOCK = 256;
 
 struct SearchTimes {
     float ms_bounds = 0.f, ms_extract = 0.f, ms_dedup = 0.f, ms_total = 0.f;
@@ -90,6 +95,9 @@ public:
     // Builds the newline side index of a chunk already resident on this device: *d_nl
     // (cudaMalloc'ed here, owned by the caller) and *n_lines.
     int build_newline_index(const uint8_t *d_text, uint32_t n, uint32_t **d_nl, uint32_t *n_lines);
+    // Builds the line directory over a newline index: (*d_dir)[j] = newlines before text byte
+    // j * LINE_BLOCK (cudaMalloc'ed here, owned by the caller).
+    int build_line_directory(const uint32_t *d_nl, uint32_t n_lines, uint32_t n, uint32_t **d_dir);
 
     // Builds the 2-byte prefix table of a resident chunk: (*d_bucket)[a << 8 | b] = first SA slot
     // whose suffix starts with bytes a, b (entry 65536 = n).  A pattern of two or more bytes is

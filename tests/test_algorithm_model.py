@@ -79,3 +79,70 @@ def test_model_with_narrow_keys_needs_more_rounds_but_same_answer(oracle):
     want = oracle.suffix_array_port(t).tolist()
     for bits in (64, 16, 5):
         assert model_suffix_array(t, key_bits=bits).tolist() == want
+
+
+# ---- extraction through the line directory (csrc/search.cu: line_directory_kernel, entry_bounds_dir) ----
+LINE_BLOCK = 256
+
+
+def model_entry_bounds_dir(nl, dirv, n, pos):
+    """Statement-for-statement model of entry_bounds_dir: nine offsets nl[lo-1 .. lo+8) decide,
+    else a search inside the rest of the block."""
+    L = len(nl)
+    if L == 0:
+        return 0, n - 1
+    blk = pos // LINE_BLOCK
+    lo = int(dirv[blk])
+    e, b = 0xFFFFFFFF, 0
+    for j in range(9):
+        idx = lo + j - 1
+        v = int(nl[idx]) if 0 <= idx < L else 0xFFFFFFFF
+        if v < pos:
+            b = v + 1
+        else:
+            e = min(e, v)
+    if e == 0xFFFFFFFF:
+        if lo + 8 >= L:
+            e = n - 1
+        else:
+            lo2, hi = lo + 8, int(dirv[blk + 1])
+            while lo2 < hi:
+                mid = lo2 + ((hi - lo2) >> 1)
+                if nl[mid] < pos:
+                    lo2 = mid + 1
+                else:
+                    hi = mid
+            e = int(nl[lo2]) if lo2 < L else n - 1
+            b = int(nl[lo2 - 1]) + 1
+    return b, e
+
+
+def reference_entry_bounds(t, pos):
+    """lib.rs:266-273: first '\\n' at or after pos (none: len - 1); 1 + last '\\n' before pos (none: 0)."""
+    n = len(t)
+    e = t.find(b"\n", pos)
+    e = n - 1 if e < 0 else e
+    b = t.rfind(b"\n", 0, pos) + 1
+    return b, e
+
+
+def test_line_directory_model_matches_reference_scans():
+    rng = np.random.default_rng(11)
+    texts = [b"\n" * 700, b"a" * 1000, b"ab\n", b"x", b"\n", b"a" * 255 + b"\n" + b"b" * 300 + b"\n\n\n" + b"c" * 513]
+    for p_nl in (0.5, 0.1, 0.02, 0.001):
+        for n in (1, 255, 256, 257, 2049, 5000):
+            a = rng.integers(97, 100, size=n, dtype=np.uint8)
+            a[rng.random(n) < p_nl] = 10
+            texts.append(a.tobytes())
+            a2 = a.copy()
+            a2[-1] = 10                       # Writer-made chunks end in '\n'
+            texts.append(a2.tobytes())
+    for t in texts:
+        n = len(t)
+        arr = np.frombuffer(t, dtype=np.uint8)
+        nl = np.flatnonzero(arr == 10).astype(np.int64)
+        n_dir = (n + LINE_BLOCK - 1) // LINE_BLOCK + 1
+        dirv = np.searchsorted(nl, np.arange(n_dir, dtype=np.int64) * LINE_BLOCK, side="left")  # line_directory_kernel
+        assert dirv[-1] == len(nl)
+        for pos in (range(n) if n <= 600 else rng.integers(0, n, size=600)):
+            assert model_entry_bounds_dir(nl, dirv, n, int(pos)) == reference_entry_bounds(t, int(pos)), (n, int(pos))
