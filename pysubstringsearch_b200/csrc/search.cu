@@ -56,23 +56,38 @@ __device__ __forceinline__ void warp_bounds(const uint8_t *__restrict__ text, co
         lo     = min(__ldg(bucket + key), n);                 // clamped: a corrupt index must not send probes out of range
         hi_all = min(max(__ldg(bucket + key + 1), lo), n);
     }
-    // smallest slot whose suffix is >= P (as a prefix comparison)
-    uint32_t hi = hi_all;
-    while (lo < hi) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        if (cmp_suffix(text, n, (uint32_t)__ldg(sa + mid), P, m, pc0, lane) < 0) lo = mid + 1;
-        else hi = mid;
-    }
-    const uint32_t lb = lo;
-    // smallest slot past lb whose suffix is > P and does not start with it
-    hi = hi_all;
-    while (lo < hi) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        if (cmp_suffix(text, n, (uint32_t)__ldg(sa + mid), P, m, pc0, lane) <= 0) lo = mid + 1;
-        else hi = mid;
-    }
+    // A probe is two dependent DRAM round trips: SA[mid], then the text it points to.  The SA
+    // slots of BOTH possible next probes are therefore requested while the text of this one is
+    // still on its way (uniform addresses: one sector each), so that a level costs one round
+    // trip instead of two — the kernel is bound by that latency (ncu: one load in flight per
+    // warp, 1 TB/s of random sectors), not by the extra sector.
+    // UPPER = false: smallest slot whose suffix is >= P (as a prefix comparison);
+    // UPPER = true : smallest slot whose suffix is > P and does not start with it.
+    auto bisect = [&](uint32_t lo_, uint32_t hi_, const bool upper) -> uint32_t {
+        if (lo_ >= hi_) return lo_;
+        uint32_t mid = lo_ + ((hi_ - lo_) >> 1);
+        uint32_t s   = (uint32_t)__ldg(sa + mid);
+        while (true) {
+            const uint32_t ml = lo_ + ((mid - lo_) >> 1), mr = (mid + 1) + ((hi_ - (mid + 1)) >> 1);
+            const bool vl = lo_ < mid, vr = mid + 1 < hi_;
+            const uint32_t sl = vl ? (uint32_t)__ldg(sa + ml) : 0u;
+            const uint32_t sr = vr ? (uint32_t)__ldg(sa + mr) : 0u;
+            const int c = cmp_suffix(text, n, s, P, m, pc0, lane);
+            if (upper ? c <= 0 : c < 0) {
+                lo_ = mid + 1;
+                if (!vr) return lo_;
+                mid = mr; s = sr;
+            } else {
+                hi_ = mid;
+                if (!vl) return lo_;
+                mid = ml; s = sl;
+            }
+        }
+    };
+    const uint32_t lb = bisect(lo, hi_all, false);
+    const uint32_t ub = bisect(lb, hi_all, true);    // starts from the lower bound (lib.rs:235)
     *lb_out  = lb;
-    *cnt_out = lo - lb;
+    *cnt_out = ub - lb;
 }
 
 __global__ void __launch_bounds__(BD_THREADS)
@@ -91,6 +106,100 @@ bounds_kernel(const DeviceChunk *__restrict__ chunks, int nc, const uint8_t *__r
     if (lane == 0) {
         lb_out[pair]  = lb;
         cnt_out[pair] = cnt;
+    }
+}
+
+// Several (query, chunk) pairs per warp: G lanes own one pair and compare G text bytes per
+// step, the 32 / G pairs of a warp advance in lockstep (every loop condition is a warp vote,
+// every ballot / shuffle runs with the full mask).  Patterns are short (config 2: 4-32 bytes),
+// so a whole warp per pair left most lanes idle AND left the kernel with one dependent load
+// chain per warp; this form keeps 32 / G chains (plus their look-ahead SA loads) in flight per
+// warp at the same occupancy.  Same searches, same results as warp_bounds.
+template <int G, bool LOOKAHEAD>
+__global__ void __launch_bounds__(BD_THREADS)
+bounds_group_kernel(const DeviceChunk *__restrict__ chunks, int nc, const uint8_t *__restrict__ patterns,
+                    const int64_t *__restrict__ pat_off, uint32_t npairs, uint32_t *__restrict__ lb_out,
+                    uint32_t *__restrict__ cnt_out) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    constexpr uint32_t GM   = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+    const uint32_t lane   = lane_id();
+    const uint32_t sub    = lane % G;              // byte of the window this lane owns
+    const uint32_t gbase  = lane - sub;            // first lane of the group
+    const uint32_t pair   = (blockIdx.x * BD_THREADS + threadIdx.x) / G;
+    const bool     valid  = pair < npairs;
+    const uint32_t q = valid ? pair / (uint32_t)nc : 0u, c = valid ? pair % (uint32_t)nc : 0u;
+    const uint8_t *__restrict__ text = chunks[c].text;
+    const int32_t *__restrict__ sa   = chunks[c].sa;
+    const uint32_t n = chunks[c].n;
+    const uint32_t *__restrict__ bucket = chunks[c].bucket;
+    int64_t o0 = 0, o1 = 0;
+    if (valid) { o0 = pat_off[q]; o1 = pat_off[q + 1]; }
+    const uint8_t *__restrict__ P = patterns + o0;
+    const uint32_t m   = o1 > o0 ? (uint32_t)min(o1 - o0, (int64_t)0x7FFFFFFF) : 0u;
+    const uint32_t pc0 = sub < m ? (uint32_t)__ldg(P + sub) : 0u;
+
+    uint32_t lo = 0, hi_all = n;
+    if (valid && bucket != nullptr && m >= 2) {
+        const uint32_t key = ((uint32_t)__ldg(P) << 8) | (uint32_t)__ldg(P + 1);
+        lo     = min(__ldg(bucket + key), n);
+        hi_all = min(max(__ldg(bucket + key + 1), lo), n);
+    }
+    uint32_t hi = hi_all, lb = 0, ub = 0;
+    int phase = valid ? 0 : 2;                     // 0 lower bound, 1 upper bound, 2 done
+    bool have = false;                             // (mid, s) is the next probe of [lo, hi)
+    uint32_t mid = 0, s = 0;
+    if (phase == 0 && lo < hi) {
+        mid = lo + ((hi - lo) >> 1);
+        s = (uint32_t)__ldg(sa + mid);
+        have = true;
+    }
+    while (true) {
+        if (phase == 0 && !have) {                 // lower bound found: the upper search starts from it (lib.rs:235)
+            lb = lo; hi = hi_all; phase = 1;
+            if (lo < hi) {
+                mid = lo + ((hi - lo) >> 1);
+                s = (uint32_t)__ldg(sa + mid);
+                have = true;
+            }
+        }
+        if (phase == 1 && !have) { ub = lo; phase = 2; }
+        const bool probing = phase < 2;
+        if (!__any_sync(FULL, probing)) break;
+        // SA slots of both possible next probes, requested before this probe's text arrives
+        const uint32_t ml = lo + ((mid - lo) >> 1), mr = (mid + 1) + ((hi - (mid + 1)) >> 1);
+        const bool vl = probing && lo < mid, vr = probing && mid + 1 < hi;
+        uint32_t sl = 0, sr = 0;
+        if (LOOKAHEAD) {
+            sl = vl ? (uint32_t)__ldg(sa + ml) : 0u;
+            sr = vr ? (uint32_t)__ldg(sa + mr) : 0u;
+        }
+        // suffix at s versus P, G bytes per step (cmp_suffix's rules)
+        const uint32_t avail = n - s;
+        int res = 2;                               // undecided
+        for (uint32_t w = 0;; w += G) {
+            const bool need = probing && res == 2 && w < m;
+            if (!__any_sync(FULL, need)) break;
+            const uint32_t b   = w + sub;
+            const bool in_pat  = need && b < m;
+            const uint32_t pc  = (w == 0) ? pc0 : (in_pat ? (uint32_t)__ldg(P + b) : 0u);
+            const bool in_txt  = in_pat && b < avail;
+            const uint32_t tc  = in_txt ? (uint32_t)__ldg(text + s + b) : 0u;
+            const bool neq     = in_pat && (!in_txt || tc != pc);
+            const uint32_t msk = (__ballot_sync(FULL, neq) >> gbase) & GM;
+            const uint32_t enc = (in_txt ? 0u : 0x10000u) | (tc << 8) | pc;
+            const uint32_t e   = __shfl_sync(FULL, enc, gbase + (msk ? __ffs(msk) - 1 : 0));
+            if (need && msk) res = (e & 0x10000u) ? -1 : (((e >> 8) & 0xFFu) < (e & 0xFFu) ? -1 : 1);
+        }
+        if (res == 2) res = 0;                     // P is a prefix of the suffix
+        if (probing) {
+            if (phase ? res <= 0 : res < 0) { lo = mid + 1; have = vr; mid = mr; s = sr; }
+            else                            { hi = mid;     have = vl; mid = ml; s = sl; }
+            if (!LOOKAHEAD && have) s = (uint32_t)__ldg(sa + mid);
+        }
+    }
+    if (valid && sub == 0) {
+        lb_out[pair]  = lb;
+        cnt_out[pair] = ub - lb;
     }
 }
 
@@ -1063,6 +1172,7 @@ int Searcher::init(int device) {
                                       (int)(4 * MEDIUM_MAX * sizeof(uint32_t))));
     small_path_ = true;
     if (const char *e = std::getenv("PSS_SMALL_PATH")) small_path_ = std::atoi(e) != 0;
+    if (const char *e = std::getenv("PSS_BOUNDS_GROUP")) bounds_group_ = std::atoi(e);
     PSS_TRY(sorter_.init(device_));
     PSS_TRY(ensure_pairs(SMALL_MAX_PAIRS, SMALL_MAX_QUERIES));
     return PSS_OK;
@@ -1356,8 +1466,33 @@ int Searcher::search(const uint8_t *d_patterns, const int64_t *d_offsets, int32_
 
     // ---- bounds + hit offsets, one host read: the number of matching suffixes ----------------
     PSS_CUDA_TRY(cudaEventRecord(ev_[0], s));
-    bounds_kernel<<<(unsigned)div_up((int64_t)npairs * 32, BD_THREADS), BD_THREADS, 0, s>>>(
-        d_chunks_, nc, d_patterns, d_offsets, npairs, d_lb_, d_cnt_);
+    // Lanes per (query, chunk) pair, measured on a 2^29-byte chunk (profiles/r02_search_bounds_ab.txt):
+    // up to about two warps' worth of pairs per warp slot the kernel is one dependent chain per
+    // pair — a whole warp per pair with the SA look-ahead is fastest (10 k pairs: 0.071 ms vs
+    // 0.09-0.12 ms grouped); far above that it is bound by random-sector throughput, where the
+    // look-ahead's extra sector per level costs more than it hides and more pairs per warp win
+    // (150 k pairs: 0.715 ms warp-per-pair without look-ahead, 0.504 with, 0.375 / 0.347 ms with
+    // 8 / 4 lanes per pair and no look-ahead).
+    int group = bounds_group_;
+    if (group == 0) group = npairs < 16384u ? 32 : (npairs < 65536u ? -8 : -4);
+    if (group == 8)
+        bounds_group_kernel<8, true><<<(unsigned)div_up((int64_t)npairs * 8, BD_THREADS), BD_THREADS, 0, s>>>(
+            d_chunks_, nc, d_patterns, d_offsets, npairs, d_lb_, d_cnt_);
+    else if (group == -8)
+        bounds_group_kernel<8, false><<<(unsigned)div_up((int64_t)npairs * 8, BD_THREADS), BD_THREADS, 0, s>>>(
+            d_chunks_, nc, d_patterns, d_offsets, npairs, d_lb_, d_cnt_);
+    else if (group == 4)
+        bounds_group_kernel<4, true><<<(unsigned)div_up((int64_t)npairs * 4, BD_THREADS), BD_THREADS, 0, s>>>(
+            d_chunks_, nc, d_patterns, d_offsets, npairs, d_lb_, d_cnt_);
+    else if (group == -4)
+        bounds_group_kernel<4, false><<<(unsigned)div_up((int64_t)npairs * 4, BD_THREADS), BD_THREADS, 0, s>>>(
+            d_chunks_, nc, d_patterns, d_offsets, npairs, d_lb_, d_cnt_);
+    else if (group == -32)
+        bounds_group_kernel<32, false><<<(unsigned)div_up((int64_t)npairs * 32, BD_THREADS), BD_THREADS, 0, s>>>(
+            d_chunks_, nc, d_patterns, d_offsets, npairs, d_lb_, d_cnt_);
+    else
+        bounds_kernel<<<(unsigned)div_up((int64_t)npairs * 32, BD_THREADS), BD_THREADS, 0, s>>>(
+            d_chunks_, nc, d_patterns, d_offsets, npairs, d_lb_, d_cnt_);
     PSS_LAUNCH_CHECK();
     PSS_CUDA_TRY(cudaEventRecord(ev_[1], s));
     hit_offsets_kernel<<<1, SCAN_THREADS, 0, s>>>(d_cnt_, npairs, d_hit_off_, d_heavy_off_, d_med_list_,

@@ -164,6 +164,8 @@ private:
     unsigned char *h_small_out_ = nullptr;   // mapped pinned result block of the small path
     uint32_t  small_seq_ = 0;
     bool      small_path_ = true;
+    int       bounds_group_ = 0;     // lanes per (query, chunk) pair of the batched bounds kernel (PSS_BOUNDS_GROUP): 0 = by
+                                     // batch size, 32 / 8 / 4 with the SA look-ahead, -32 / -8 / -4 without
     cudaEvent_t ev_[8] = {};
     struct Deferred {
         bool     valid = false;

@@ -170,6 +170,18 @@ def test_writer_multichunk_vs_oracle(pss, oracle):
         w.add_entries_from_file_lines(src)
         w.close()
         assert open(a, "rb").read() == open(b, "rb").read()
+        # LF-only files take the bulk-append path (whole runs of lines per copy): chunk boundaries
+        # must still fall where the per-line flush rule puts them, for chunk sizes far below and
+        # above the 1 MiB read block, with and without a final newline
+        for tail, mcl in ((b"\n", 4096), (b"", 300_000), (b"\n", 1_500_000), (b"", None)):
+            open(src, "wb").write(b"\n".join(entries[:30000]) + tail)
+            w = pss.Writer(a, mcl)
+            assert w.add_entries_from_file_lines(src) == 0
+            w.close()
+            w = oracle.Writer(b, mcl)
+            w.add_entries_from_file_lines(src)
+            w.close()
+            assert open(a, "rb").read() == open(b, "rb").read(), (tail, mcl)
 
 
 def test_writer_overlong_file_line_grows_capacity(pss, oracle):
@@ -259,6 +271,33 @@ def test_search_random_patterns_vs_oracle(pss, oracle):
                 _compare_searches(r, o, [pat])
             r.close()
             o.close()
+
+
+@pytest.mark.parametrize("env", [{"PSS_BOUNDS_GROUP": "-4"}, {"PSS_BOUNDS_GROUP": "4"}, {"PSS_BOUNDS_GROUP": "-8"},
+                                 {"PSS_BOUNDS_GROUP": "8"}, {"PSS_BOUNDS_GROUP": "-32"}, {"PSS_BOUNDS_GROUP": "32"},
+                                 {"PSS_LINE_DIR": "0"}])
+def test_search_kernel_variants_vs_oracle(pss, oracle, env, monkeypatch):
+    """The batched bounds kernel picks its geometry by batch size (a warp per pair below 16 384
+    pairs, 8 or 4 lanes per pair above) and extraction goes through the line directory; every
+    variant is forced here on the same patterns — empty, '\\n', longer than any window, absent,
+    crossing entries — and compared with the oracle's ordered tuples."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)               # read when the Reader is opened
+    monkeypatch.setenv("PSS_SMALL_PATH", "0")  # one-query batches through the batched kernels as well
+    text = synth.zipf_words_text(3_000_000, seed=32, vocab=2048, block=1 << 16)
+    entries = bytes(text).split(b"\n")[:-1]
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "v.idx")
+        _write(oracle.Writer, p, entries, 1 << 20)       # 3 chunks
+        r, o = pss.Reader(p), oracle.Reader(p)
+        pats = synth.config2_queries(text, nq=400, seed=5)
+        pats += [b"", b"\n", b"e ", b"zzzzzz", b"a", b" ", b"\n\n", bytes(text[1000:1100]), bytes(text[5000:5033]),
+                 bytes(text[7000:7004]), bytes(text[7000:7005]), bytes(text[len(text) - 9:]), b"q" * 300]
+        _compare_searches(r, o, pats)
+        for pat in pats[::40]:
+            _compare_searches(r, o, [pat])
+        r.close()
+        o.close()
 
 
 def test_search_binary_text_and_long_lines(pss, oracle):

@@ -41,7 +41,8 @@ for _ in range(repeat):
             print("  round %d shift %2d spread %5.1f n=%10d %.3f ms %7.1f GB/s" % (q.round, q.shift, q.reserved / 1000.0, q.n_records, q.ms, 24.0 * q.n_records / (q.ms * 1e-3) / 1e9))
 if do_search:
     pats = synth.config2_queries(text, nq=10000, seed=7)
-    pats += [b"sojq", b"google", b"e "]
+    rep = int(os.environ.get("PSS_PROFILE_QUERY_REPEAT", "1"))   # 15: as many (query, chunk) pairs as config 3 has
+    pats = pats * rep if rep > 1 else pats + [b"sojq", b"google", b"e "]
     with tempfile.TemporaryDirectory() as d:
         p = os.path.join(d, "p.idx")
         with open(p, "wb") as f:

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
-"""A/B of the extraction step on one config-3 chunk: PSS_LINE_DIR=0 (text scans) vs 1 (line
-directory).  Builds the chunk's suffix array once, opens the index twice and runs the same
+"""A/B of the search kernels' variants on one config-3 chunk: PSS_LINE_DIR=0 (extraction scans
+the text) vs 1 (line directory), PSS_BOUNDS_GROUP=32 (one warp per pair) vs 16 / 8 lanes per
+pair.  Builds the chunk's suffix array once, opens the index once per variant and runs the same
 10 000-query batch (plus one high-hit bigram) through the C ABI, printing the stage times and
-checking that both readers return identical tuples.  usage: search_ab.py [n_bytes] [repeat]"""
+checking that every variant returns identical tuples.  usage: search_ab.py [n_bytes] [repeat]"""
 import os
 import sys
 import tempfile
@@ -24,21 +25,28 @@ with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") els
     with open(p, "wb") as f:
         f.write(np.uint32(n).tobytes()); f.write(memoryview(text)); f.write(np.uint32(4 * n).tobytes()); f.write(memoryview(sa))
     results = {}
-    for mode in ("0", "1"):
-        os.environ["PSS_LINE_DIR"] = mode
+    modes = [("dir1 g32", {"PSS_LINE_DIR": "1", "PSS_BOUNDS_GROUP": "32"}),
+             ("dir1 g32 no-lookahead", {"PSS_LINE_DIR": "1", "PSS_BOUNDS_GROUP": "-32"}),
+             ("dir1 g8", {"PSS_LINE_DIR": "1", "PSS_BOUNDS_GROUP": "8"}),
+             ("dir1 g8 no-lookahead", {"PSS_LINE_DIR": "1", "PSS_BOUNDS_GROUP": "-8"}),
+             ("dir1 g4", {"PSS_LINE_DIR": "1", "PSS_BOUNDS_GROUP": "4"}),
+             ("dir1 g4 no-lookahead", {"PSS_LINE_DIR": "1", "PSS_BOUNDS_GROUP": "-4"})]
+    for mode, env in modes:
+        os.environ.update(env)
         r = pss.Reader(p)
-        for label, batch in (("10k batch", pats), ("bigram", [b"e "]), ("google", [b"google"])):
+        for label, batch in (("10k batch", pats), ("150k batch", pats * 15), ("bigram", [b"e "]), ("google", [b"google"])):
             best = None
             for _ in range(repeat):
                 qo, ch, st, en, stats = r.search_batch(batch)
                 if best is None or stats["ms_total"] < best["ms_total"]:
                     best = stats
             results[(mode, label)] = (qo, ch, st, en)
-            print("PSS_LINE_DIR=%s %-9s entries=%d hits=%d bounds %.3f extract %.3f dedup %.3f total %.3f ms" % (
+            print("%-22s %-10s entries=%d hits=%d bounds %.3f extract %.3f dedup %.3f total %.3f ms" % (
                 mode, label, len(ch), best["n_hits"], best["ms_bounds"], best["ms_extract"], best["ms_dedup"], best["ms_total"]))
         r.close()
-    for label in ("10k batch", "bigram", "google"):
-        a, b = results[("0", label)], results[("1", label)]
-        same = all(np.array_equal(x, y) for x, y in zip(a, b))
-        print("identical tuples (%s): %s" % (label, same))
-        assert same
+    for label in ("10k batch", "150k batch", "bigram", "google"):
+        for mode, _ in modes[1:]:
+            a, b = results[(modes[0][0], label)], results[(mode, label)]
+            same = all(np.array_equal(x, y) for x, y in zip(a, b))
+            print("identical tuples (%s, %s vs %s): %s" % (label, mode, modes[0][0], same))
+            assert same
