@@ -203,11 +203,7 @@ bounds_group_kernel(const DeviceChunk *__restrict__ chunks, int nc, const uint8_
     }
 }
 
-// ------------------------------------------------------------------------------------
-// Single-CTA scans over per-pair arrays (npairs is small next to the hit count): thread t
-// owns a contiguous range, the partials are scanned in shared memory.
-// ------------------------------------------------------------------------------------
-constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_THREADS = 1024;   // single-CTA scan over the compaction's tile sums (tile_scan_kernel)
 
 // Dedup tiers by the number of matching suffixes h of a (query, chunk) pair:
 //   light   h <= LIGHT_MAX    one warp, all-pairs compare in shared memory    (pair_dedup_kernel)
@@ -217,86 +213,168 @@ constexpr int SCAN_THREADS = 1024;
 constexpr uint32_t LIGHT_MAX  = 256;
 constexpr uint32_t MEDIUM_MAX = 8192;
 
+// ------------------------------------------------------------------------------------
+// Scans over the per-pair arrays, PS_TILE pairs per CTA in two launches each: per-CTA partials,
+// then every CTA folds the partials of the CTAs before (after) it and scans its own tile.
+// (One 1024-thread CTA walking the whole array — a thread per contiguous range, one sector per
+// load — took 0.25 + 0.14 ms of a 150 000-pair batch whose other kernels add up to 1.1 ms.)
+// ------------------------------------------------------------------------------------
+constexpr int PS_THREADS = 256;
+constexpr int PS_IPT     = 8;
+constexpr int PS_TILE    = PS_THREADS * PS_IPT;
+
+struct Tri {
+    unsigned long long h, v;   // hits, hits of heavy pairs
+    uint32_t m;                // medium pairs
+};
+__device__ __forceinline__ Tri tri_add(const Tri &a, const Tri &b) { return Tri{a.h + b.h, a.v + b.v, a.m + b.m}; }
+__device__ __forceinline__ Tri tri_of(uint32_t c) {
+    return Tri{c, c > MEDIUM_MAX ? c : 0ull, (c > LIGHT_MAX && c <= MEDIUM_MAX) ? 1u : 0u};
+}
+// Sum over the block, returned to every thread; *excl = the sum over the threads before this one.
+__device__ __forceinline__ Tri tri_block_scan(const Tri &mine, Tri *s_warp, Tri *excl) {
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    Tri incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        Tri y{__shfl_up_sync(0xffffffffu, incl.h, o), __shfl_up_sync(0xffffffffu, incl.v, o),
+              __shfl_up_sync(0xffffffffu, incl.m, o)};
+        if (lane >= (uint32_t)o) incl = tri_add(incl, y);
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    Tri pre{0, 0, 0}, tot{0, 0, 0};
+#pragma unroll
+    for (int w = 0; w < PS_THREADS / 32; ++w) {
+        const Tri t = s_warp[w];
+        if ((uint32_t)w < warp) pre = tri_add(pre, t);
+        tot = tri_add(tot, t);
+    }
+    __syncthreads();
+    *excl = Tri{pre.h + incl.h - mine.h, pre.v + incl.v - mine.v, pre.m + incl.m - mine.m};
+    return tot;
+}
+
+// partials[b] = (hits, heavy hits, medium pairs) of the pairs of tile b
+__global__ void __launch_bounds__(PS_THREADS)
+hit_partials_kernel(const uint32_t *__restrict__ cnt, uint32_t npairs, Tri *__restrict__ partials) {
+    __shared__ Tri s_warp[PS_THREADS / 32];
+    const uint32_t base = blockIdx.x * PS_TILE + threadIdx.x * PS_IPT;
+    Tri mine{0, 0, 0};
+#pragma unroll
+    for (int e = 0; e < PS_IPT; ++e)
+        if (base + e < npairs) mine = tri_add(mine, tri_of(__ldg(cnt + base + e)));
+    Tri excl;
+    const Tri tot = tri_block_scan(mine, s_warp, &excl);
+    if (threadIdx.x == 0) partials[blockIdx.x] = tot;
+}
+
 // hit_off[p] = sum of cnt[0..p) (u32, wraps only when the batch is oversized, which the
 // u64 total reveals); hit_off[npairs] = total.  heavy_off[p] = the same scan over the heavy
 // pairs only (where pair p's hits go in the sort's input); med_list = the medium pairs, in order.
 // totals[0] = all hits, totals[1] = hits of heavy pairs, totals[2] = number of medium pairs.
-__global__ void __launch_bounds__(SCAN_THREADS)
-hit_offsets_kernel(const uint32_t *__restrict__ cnt, uint32_t npairs, uint32_t *__restrict__ hit_off,
-                   uint32_t *__restrict__ heavy_off, uint32_t *__restrict__ med_list,
+__global__ void __launch_bounds__(PS_THREADS)
+hit_offsets_kernel(const uint32_t *__restrict__ cnt, uint32_t npairs, const Tri *__restrict__ partials,
+                   uint32_t *__restrict__ hit_off, uint32_t *__restrict__ heavy_off, uint32_t *__restrict__ med_list,
                    unsigned long long *__restrict__ totals) {
-    __shared__ unsigned long long s_part[SCAN_THREADS], s_heavy[SCAN_THREADS];
-    __shared__ uint32_t s_med[SCAN_THREADS];
-    const uint32_t per = (npairs + SCAN_THREADS - 1) / SCAN_THREADS;
-    const uint32_t lo  = min(npairs, threadIdx.x * per), hi = min(npairs, lo + per);
-    unsigned long long sum = 0, hsum = 0;
-    uint32_t msum = 0;
-    for (uint32_t p = lo; p < hi; ++p) {
-        const uint32_t c = cnt[p];
-        sum += c;
-        if (c > MEDIUM_MAX) hsum += c;
-        else if (c > LIGHT_MAX) ++msum;
+    __shared__ Tri s_warp[PS_THREADS / 32];
+    // everything before this tile
+    Tri before{0, 0, 0};
+    for (uint32_t j = threadIdx.x; j < blockIdx.x; j += PS_THREADS) before = tri_add(before, partials[j]);
+    Tri unused;
+    before = tri_block_scan(before, s_warp, &unused);
+    // this tile
+    const uint32_t base = blockIdx.x * PS_TILE + threadIdx.x * PS_IPT;
+    uint32_t c[PS_IPT];
+    Tri mine{0, 0, 0};
+#pragma unroll
+    for (int e = 0; e < PS_IPT; ++e) {
+        c[e] = base + e < npairs ? __ldg(cnt + base + e) : 0u;
+        mine = tri_add(mine, tri_of(c[e]));
     }
-    s_part[threadIdx.x]  = sum;
-    s_heavy[threadIdx.x] = hsum;
-    s_med[threadIdx.x]   = msum;
-    __syncthreads();
-    for (int o = 1; o < SCAN_THREADS; o <<= 1) {
-        unsigned long long y = threadIdx.x >= (uint32_t)o ? s_part[threadIdx.x - o] : 0ull;
-        unsigned long long z = threadIdx.x >= (uint32_t)o ? s_heavy[threadIdx.x - o] : 0ull;
-        uint32_t w = threadIdx.x >= (uint32_t)o ? s_med[threadIdx.x - o] : 0u;
-        __syncthreads();
-        s_part[threadIdx.x] += y;
-        s_heavy[threadIdx.x] += z;
-        s_med[threadIdx.x] += w;
-        __syncthreads();
+    Tri run;
+    const Tri tot = tri_block_scan(mine, s_warp, &run);
+    run = tri_add(run, before);
+#pragma unroll
+    for (int e = 0; e < PS_IPT; ++e) {
+        const uint32_t p = base + e;
+        if (p >= npairs) break;
+        hit_off[p]   = (uint32_t)run.h;
+        heavy_off[p] = (uint32_t)run.v;
+        if (c[e] > LIGHT_MAX && c[e] <= MEDIUM_MAX) med_list[run.m] = p;
+        run = tri_add(run, tri_of(c[e]));
     }
-    unsigned long long run = s_part[threadIdx.x] - sum, hrun = s_heavy[threadIdx.x] - hsum;
-    uint32_t mrun = s_med[threadIdx.x] - msum;
-    for (uint32_t p = lo; p < hi; ++p) {
-        const uint32_t c = cnt[p];
-        hit_off[p]   = (uint32_t)run;
-        heavy_off[p] = (uint32_t)hrun;
-        run += c;
-        if (c > MEDIUM_MAX) hrun += c;
-        else if (c > LIGHT_MAX) med_list[mrun++] = p;
-    }
-    if (threadIdx.x == SCAN_THREADS - 1) {
-        hit_off[npairs] = (uint32_t)s_part[SCAN_THREADS - 1];
-        totals[0]       = s_part[SCAN_THREADS - 1];
-        totals[1]       = s_heavy[SCAN_THREADS - 1];
-        totals[2]       = s_med[SCAN_THREADS - 1];
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        const Tri all = tri_add(before, tot);
+        hit_off[npairs] = (uint32_t)all.h;
+        totals[0]       = all.h;
+        totals[1]       = all.v;
+        totals[2]       = all.m;
     }
 }
 
 // pair_first[p] = output offset of pair p's first entry, 0xFFFFFFFF for pairs without hits
 // (written by compact_kernel).  entry_off[p] = base + entries before pair p = the first
 // offset of the next pair that has hits (suffix minimum), or the sub-batch total.
-__global__ void __launch_bounds__(SCAN_THREADS)
-entry_offsets_kernel(const uint32_t *__restrict__ pair_first, uint32_t np, const uint32_t *__restrict__ kept_total,
-                     uint32_t base, uint32_t *__restrict__ entry_off) {
-    __shared__ uint32_t s_part[SCAN_THREADS];
-    const uint32_t per = (np + SCAN_THREADS - 1) / SCAN_THREADS;
-    const uint32_t lo  = min(np, threadIdx.x * per), hi = min(np, lo + per);
-    uint32_t mn = 0xFFFFFFFFu;
-    for (uint32_t p = lo; p < hi; ++p) mn = min(mn, pair_first[p]);
-    s_part[threadIdx.x] = mn;
+__device__ __forceinline__ uint32_t block_min_256(uint32_t v, uint32_t *s_warp) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane_id() == 0) s_warp[threadIdx.x >> 5] = v;
     __syncthreads();
-    // suffix minimum over the partials (Hillis-Steele, looking right)
-    for (int o = 1; o < SCAN_THREADS; o <<= 1) {
-        uint32_t y = threadIdx.x + o < SCAN_THREADS ? s_part[threadIdx.x + o] : 0xFFFFFFFFu;
-        __syncthreads();
-        s_part[threadIdx.x] = min(s_part[threadIdx.x], y);
-        __syncthreads();
-    }
+    uint32_t r = 0xFFFFFFFFu;
+#pragma unroll
+    for (int w = 0; w < PS_THREADS / 32; ++w) r = min(r, s_warp[w]);
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(PS_THREADS)
+pair_first_min_kernel(const uint32_t *__restrict__ pair_first, uint32_t np, uint32_t *__restrict__ part_min) {
+    __shared__ uint32_t s_warp[PS_THREADS / 32];
+    const uint32_t base = blockIdx.x * PS_TILE + threadIdx.x * PS_IPT;
+    uint32_t mn = 0xFFFFFFFFu;
+#pragma unroll
+    for (int e = 0; e < PS_IPT; ++e)
+        if (base + e < np) mn = min(mn, __ldg(pair_first + base + e));
+    mn = block_min_256(mn, s_warp);
+    if (threadIdx.x == 0) part_min[blockIdx.x] = mn;
+}
+
+__global__ void __launch_bounds__(PS_THREADS)
+entry_offsets_kernel(const uint32_t *__restrict__ pair_first, uint32_t np, const uint32_t *__restrict__ part_min,
+                     const uint32_t *__restrict__ kept_total, uint32_t base, uint32_t *__restrict__ entry_off) {
+    __shared__ uint32_t s_warp[PS_THREADS / 32];
     const uint32_t total = *kept_total;
-    uint32_t carry = threadIdx.x + 1 < SCAN_THREADS ? s_part[threadIdx.x + 1] : 0xFFFFFFFFu;
-    carry = min(carry, total);
-    for (uint32_t p = hi; p > lo; --p) {
-        carry = min(carry, pair_first[p - 1]);
-        entry_off[p - 1] = base + carry;
+    // the first entry of any later tile (or the total)
+    uint32_t after = total;
+    for (uint32_t j = blockIdx.x + 1 + threadIdx.x; j < gridDim.x; j += PS_THREADS) after = min(after, part_min[j]);
+    after = block_min_256(after, s_warp);
+    const uint32_t at = blockIdx.x * PS_TILE + threadIdx.x * PS_IPT;
+    uint32_t v[PS_IPT];
+#pragma unroll
+    for (int e = 0; e < PS_IPT; ++e) v[e] = at + e < np ? __ldg(pair_first + at + e) : 0xFFFFFFFFu;
+#pragma unroll
+    for (int e = PS_IPT - 2; e >= 0; --e) v[e] = min(v[e], v[e + 1]);      // suffix minimum inside the thread
+    // minimum over the threads after this one: inclusive suffix scan in the warp, then the later warps
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    uint32_t incl = v[0];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + (uint32_t)o < 32) incl = min(incl, y);
     }
-    if (threadIdx.x == 0) entry_off[np] = base + total;
+    if (lane == 0) s_warp[warp] = incl;
+    uint32_t later = __shfl_down_sync(0xffffffffu, incl, 1);
+    if (lane == 31) later = 0xFFFFFFFFu;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < PS_THREADS / 32; ++w)
+        if ((uint32_t)w > warp) later = min(later, s_warp[w]);
+    later = min(later, after);
+#pragma unroll
+    for (int e = 0; e < PS_IPT; ++e)
+        if (at + e < np) entry_off[at + e] = base + min(v[e], later);
+    if (blockIdx.x == 0 && threadIdx.x == 0) entry_off[np] = base + total;
 }
 
 __global__ void __launch_bounds__(256)
@@ -1184,6 +1262,8 @@ void Searcher::release() {
     cudaFree(d_chunks_);
     cudaFree(d_lb_); cudaFree(d_cnt_); cudaFree(d_hit_off_); cudaFree(d_pair_first_);
     cudaFree(d_entry_off_); cudaFree(d_query_off_); cudaFree(d_heavy_off_); cudaFree(d_start_); cudaFree(d_med_list_); cudaFree(d_big_list_);
+    cudaFree(d_scan_part_);
+    d_scan_part_ = nullptr;
     if (h_cnt_) cudaFreeHost(h_cnt_);
     if (h_hit_off_) cudaFreeHost(h_hit_off_);
     if (h_heavy_off_) cudaFreeHost(h_heavy_off_);
@@ -1298,7 +1378,8 @@ int Searcher::build_prefix_buckets(const uint8_t *d_text, const int32_t *d_sa, u
 int Searcher::ensure_pairs(int64_t npairs, int64_t nq) {
     if (npairs > pair_cap_) {
         cudaFree(d_lb_); cudaFree(d_cnt_); cudaFree(d_hit_off_); cudaFree(d_pair_first_); cudaFree(d_entry_off_);
-        cudaFree(d_heavy_off_); cudaFree(d_med_list_); cudaFree(d_big_list_);
+        cudaFree(d_heavy_off_); cudaFree(d_med_list_); cudaFree(d_big_list_); cudaFree(d_scan_part_);
+        d_scan_part_ = nullptr;
         if (h_cnt_) cudaFreeHost(h_cnt_);
         if (h_hit_off_) cudaFreeHost(h_hit_off_);
         if (h_heavy_off_) cudaFreeHost(h_heavy_off_);
@@ -1315,6 +1396,7 @@ int Searcher::ensure_pairs(int64_t npairs, int64_t nq) {
         PSS_CUDA_TRY(cudaMalloc(&d_heavy_off_, (cap + 1) * sizeof(uint32_t)));
         PSS_CUDA_TRY(cudaMalloc(&d_med_list_, (cap + 1) * sizeof(uint32_t)));
         PSS_CUDA_TRY(cudaMalloc(&d_big_list_, (cap + 1) * sizeof(uint32_t)));
+        PSS_CUDA_TRY(cudaMalloc(&d_scan_part_, (size_t)(div_up(cap, PS_TILE) + 1) * sizeof(Tri)));
         pair_cap_ = cap;
     }
     if (nq > query_cap_) {
@@ -1495,8 +1577,12 @@ int Searcher::search(const uint8_t *d_patterns, const int64_t *d_offsets, int32_
             d_chunks_, nc, d_patterns, d_offsets, npairs, d_lb_, d_cnt_);
     PSS_LAUNCH_CHECK();
     PSS_CUDA_TRY(cudaEventRecord(ev_[1], s));
-    hit_offsets_kernel<<<1, SCAN_THREADS, 0, s>>>(d_cnt_, npairs, d_hit_off_, d_heavy_off_, d_med_list_,
-                                                   reinterpret_cast<unsigned long long *>(d_scalar_ + 10));
+    const unsigned ps_tiles = (unsigned)div_up(npairs, PS_TILE);
+    hit_partials_kernel<<<ps_tiles, PS_THREADS, 0, s>>>(d_cnt_, npairs, reinterpret_cast<Tri *>(d_scan_part_));
+    PSS_LAUNCH_CHECK();
+    hit_offsets_kernel<<<ps_tiles, PS_THREADS, 0, s>>>(d_cnt_, npairs, reinterpret_cast<const Tri *>(d_scan_part_), d_hit_off_,
+                                                      d_heavy_off_, d_med_list_,
+                                                      reinterpret_cast<unsigned long long *>(d_scalar_ + 10));
     PSS_LAUNCH_CHECK();
     PSS_CUDA_TRY(cudaMemcpyAsync(h_scalar_ + 10, d_scalar_ + 10, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     PSS_CUDA_TRY(cudaStreamSynchronize(s));
@@ -1622,8 +1708,15 @@ int Searcher::search(const uint8_t *d_patterns, const int64_t *d_offsets, int32_
                                                         d_out_start_ + entries, d_out_end_ + entries);
         }
         PSS_LAUNCH_CHECK();
-        entry_offsets_kernel<<<1, SCAN_THREADS, 0, s>>>(d_pair_first_, sb.np, d_scalar_ + 2, entries, d_entry_off_ + sb.a);
-        PSS_LAUNCH_CHECK();
+        {
+            const unsigned pt = (unsigned)div_up(sb.np, PS_TILE);
+            uint32_t *part_min = reinterpret_cast<uint32_t *>(d_scan_part_);
+            pair_first_min_kernel<<<pt, PS_THREADS, 0, s>>>(d_pair_first_, sb.np, part_min);
+            PSS_LAUNCH_CHECK();
+            entry_offsets_kernel<<<pt, PS_THREADS, 0, s>>>(d_pair_first_, sb.np, part_min, d_scalar_ + 2, entries,
+                                                           d_entry_off_ + sb.a);
+            PSS_LAUNCH_CHECK();
+        }
         PSS_CUDA_TRY(cudaEventRecord(ev_[4], s));
         PSS_CUDA_TRY(cudaMemcpyAsync(h_scalar_ + 2, d_scalar_ + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         PSS_CUDA_TRY(cudaMemcpyAsync(h_scalar_ + 8, sorter_.d_error_flag(), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));

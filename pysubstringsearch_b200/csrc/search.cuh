@@ -143,6 +143,7 @@ private:
     int64_t   pair_cap_ = 0, query_cap_ = 0;
     uint32_t *d_lb_ = nullptr, *d_cnt_ = nullptr, *d_hit_off_ = nullptr, *d_pair_first_ = nullptr;
     uint32_t *d_entry_off_ = nullptr, *d_heavy_off_ = nullptr, *d_med_list_ = nullptr, *d_big_list_ = nullptr;
+    void     *d_scan_part_ = nullptr;   // per-tile partials of the per-pair scans (hit offsets, entry offsets)
     int64_t  *d_query_off_ = nullptr;
     // pinned; only the oversized-batch path uses them
     uint32_t *h_cnt_ = nullptr, *h_hit_off_ = nullptr, *h_heavy_off_ = nullptr, *h_med_list_ = nullptr;
