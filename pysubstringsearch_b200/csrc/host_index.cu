@@ -372,6 +372,7 @@ pss_reader::~pss_reader() {
         cudaFree(c.d_nl);
         cudaFree(c.d_bucket);
         cudaFree(c.d_dir);
+        cudaFree(c.d_rec);
     }
     cudaFree(d_pat);
     if (ev0) cudaEventDestroy(ev0);
@@ -418,12 +419,14 @@ static int reader_finish_open(pss_reader *r) {
         ChunkHost &c = r->chunks[k];
         if (!c.owned || c.n == 0) continue;
         PSS_TRY(r->searcher.build_newline_index(c.d_text, c.n, &c.d_nl, &c.n_lines));
-        const char *use_dir = std::getenv("PSS_LINE_DIR");   // 0: extraction scans the text instead (A/B measurements)
-        if (!use_dir || std::atoi(use_dir) != 0)
-            PSS_TRY(r->searcher.build_line_directory(c.d_nl, c.n_lines, c.n, &c.d_dir));
+        // what extraction consults (A/B measurements): 2 (default) line records, 1 line directory, 0 text scans
+        const char *use_dir = std::getenv("PSS_LINE_DIR");
+        const int line_mode = use_dir ? std::atoi(use_dir) : 2;
+        if (line_mode == 1) PSS_TRY(r->searcher.build_line_directory(c.d_nl, c.n_lines, c.n, &c.d_dir));
+        else if (line_mode != 0) PSS_TRY(r->searcher.build_line_records(c.d_nl, c.n_lines, c.n, &c.d_rec));
         PSS_TRY(r->searcher.build_prefix_buckets(c.d_text, c.d_sa, c.n, &c.d_bucket));
         DeviceChunk dc = {};
-        dc.text = c.d_text; dc.sa = c.d_sa; dc.nl = c.d_nl; dc.bucket = c.d_bucket; dc.dir = c.d_dir; dc.n = c.n; dc.n_lines = c.n_lines;
+        dc.text = c.d_text; dc.sa = c.d_sa; dc.nl = c.d_nl; dc.bucket = c.d_bucket; dc.dir = c.d_dir; dc.rec = c.d_rec; dc.n = c.n; dc.n_lines = c.n_lines;
         dc.global_id = (int32_t)k;
         dchunks.push_back(dc);
     }

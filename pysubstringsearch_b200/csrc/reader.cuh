@@ -126,7 +126,8 @@ struct ChunkHost {
     int32_t  *d_sa   = nullptr;
     uint32_t *d_nl   = nullptr;            // newline side index (always ours)
     uint32_t *d_bucket = nullptr;          // 2-byte prefix table over the SA (always ours)
-    uint32_t *d_dir  = nullptr;            // line directory over d_nl (always ours)
+    uint32_t *d_dir  = nullptr;            // line directory over d_nl (always ours; PSS_LINE_DIR=1 only)
+    uint4    *d_rec  = nullptr;            // line records (always ours)
     uint32_t  n_lines = 0;
 };
 

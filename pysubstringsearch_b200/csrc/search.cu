@@ -470,6 +470,40 @@ line_directory_kernel(const uint32_t *__restrict__ nl, uint32_t n_lines, uint32_
     dir[j] = lo;
 }
 
+// Line records: one 32-byte sector per LINE_REC_BLOCK (128) text bytes that answers "which entry
+// contains position p" for every p of the block with a single load:
+//   x = start of the entry that is open at the block's first byte (1 + last '\n' before the block, 0 if none)
+//   y = first '\n' at or after the block's end, n - 1 if there is none (lib.rs:266-269: None -> len - 1)
+//   z, w, x', y' = 128-bit map of the '\n' inside the block
+// Built from the sorted newline offsets, one thread per block.
+__global__ void __launch_bounds__(256)
+line_records_kernel(const uint32_t *__restrict__ nl, uint32_t n_lines, uint32_t n, uint32_t n_blocks,
+                    uint4 *__restrict__ rec) {
+    const uint32_t j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= n_blocks) return;
+    const uint64_t at = (uint64_t)j * LINE_REC_BLOCK, end = at + LINE_REC_BLOCK;
+    uint32_t lo = 0, hi = n_lines;
+    while (lo < hi) {                                   // first newline at or after the block's start
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if ((uint64_t)__ldg(nl + mid) < at) lo = mid + 1;
+        else hi = mid;
+    }
+    uint32_t bm[4] = {0, 0, 0, 0};
+    const uint32_t open_at = lo > 0 ? __ldg(nl + lo - 1) + 1 : 0u;
+    uint32_t k = lo;
+    for (; k < n_lines; ++k) {
+        const uint64_t x = __ldg(nl + k);
+        if (x >= end) break;
+        const uint32_t o = (uint32_t)(x - at);
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+            if ((o >> 5) == (uint32_t)w) bm[w] |= 1u << (o & 31);
+    }
+    const uint32_t next = k < n_lines ? __ldg(nl + k) : n - 1;
+    rec[2 * (size_t)j]     = make_uint4(open_at, next, bm[0], bm[1]);
+    rec[2 * (size_t)j + 1] = make_uint4(bm[2], bm[3], 0u, 0u);
+}
+
 // ------------------------------------------------------------------------------------
 // 2-byte prefix table: bucket[a << 8 | b] = first SA slot whose suffix starts with a, b.
 // Boundaries are where the prefix changes along the suffix array; the thread at a boundary
@@ -572,7 +606,36 @@ __device__ __forceinline__ void entry_bounds_dir(const DeviceChunk &ch, uint32_t
     *e_out = e;
 }
 
+// With the line records (the default) ONE 32-byte sector decides: the entry's end is the first
+// set bit at or after pos in the block's newline map, else the stored next newline; its start
+// follows the last set bit before pos, else it is the stored start of the entry open at the
+// block's first byte.
+__device__ __forceinline__ void entry_bounds_rec(const DeviceChunk &ch, uint32_t pos, uint32_t *b_out, uint32_t *e_out) {
+    const uint32_t blk = pos / LINE_REC_BLOCK, off = pos % LINE_REC_BLOCK;
+    const uint4 r0 = __ldg(ch.rec + 2 * (size_t)blk), r1 = __ldg(ch.rec + 2 * (size_t)blk + 1);
+    const unsigned long long lo64 = ((unsigned long long)r0.w << 32) | r0.z, hi64 = ((unsigned long long)r1.y << 32) | r1.x;
+    const uint32_t base = blk * LINE_REC_BLOCK;
+    // at or after pos
+    unsigned long long f_lo = off < 64 ? (lo64 & (~0ull << off)) : 0ull;
+    unsigned long long f_hi = off < 64 ? hi64 : (hi64 & (~0ull << (off - 64)));
+    uint32_t e = r0.y;
+    if (f_lo) e = base + (uint32_t)__ffsll((long long)f_lo) - 1u;
+    else if (f_hi) e = base + 64u + (uint32_t)__ffsll((long long)f_hi) - 1u;
+    // strictly before pos
+    unsigned long long b_lo = off < 64 ? (off ? (lo64 & (~0ull >> (64 - off))) : 0ull) : lo64;
+    unsigned long long b_hi = off > 64 ? (hi64 & (~0ull >> (128 - off))) : 0ull;
+    uint32_t b = r0.x;
+    if (b_hi) b = base + 64u + (63u - (uint32_t)__clzll((long long)b_hi)) + 1u;
+    else if (b_lo) b = base + (63u - (uint32_t)__clzll((long long)b_lo)) + 1u;
+    *b_out = b;
+    *e_out = e;
+}
+
 __device__ __forceinline__ void entry_bounds(const DeviceChunk &ch, uint32_t pos, uint32_t *b_out, uint32_t *e_out) {
+    if (ch.rec != nullptr) {
+        entry_bounds_rec(ch, pos, b_out, e_out);
+        return;
+    }
     if (ch.dir != nullptr) {
         entry_bounds_dir(ch, pos, b_out, e_out);
         return;
@@ -1353,6 +1416,25 @@ int Searcher::build_line_directory(const uint32_t *d_nl, uint32_t n_lines, uint3
         return fail(PSS_ERR_CUDA, std::string("line directory: ") + cudaGetErrorString(e));
     }
     *d_dir = dir;
+    return PSS_OK;
+}
+
+int Searcher::build_line_records(const uint32_t *d_nl, uint32_t n_lines, uint32_t n, uint4 **d_rec) {
+    *d_rec = nullptr;
+    if (n == 0 || !d_nl) return PSS_OK;
+    PSS_CUDA_TRY(cudaSetDevice(device_));
+    const uint32_t n_blocks = (uint32_t)div_up(n, LINE_REC_BLOCK);
+    uint4 *rec = nullptr;
+    PSS_CUDA_TRY(cudaMalloc(&rec, (size_t)n_blocks * 2 * sizeof(uint4)));
+    line_records_kernel<<<(unsigned)div_up(n_blocks, 256), 256, 0, stream_>>>(d_nl, n_lines, n, n_blocks, rec);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
+    if (e != cudaSuccess) {
+        cudaFree(rec);
+        return fail(PSS_ERR_CUDA, std::string("line records: ") + cudaGetErrorString(e));
+    }
+    *d_rec = rec;
     return PSS_OK;
 }
 

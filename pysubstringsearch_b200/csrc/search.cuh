@@ -39,6 +39,7 @@ struct DeviceChunk {
     const uint32_t *nl;        // device: sorted offsets of every '\n' (may be null: unbounded scans)
     const uint32_t *bucket;    // device: [65537] first SA slot of every 2-byte prefix (may be null: full-range search)
     const uint32_t *dir;       // device: [ceil(n / LINE_BLOCK) + 1] newlines before every text block (may be null: text scans)
+    const uint4    *rec;       // device: [ceil(n / LINE_REC_BLOCK)][2] line records, one sector per text block (may be null: dir / scans)
     uint32_t        n;
     uint32_t        n_lines;   // entries of nl
     int32_t         global_id;
@@ -48,6 +49,9 @@ struct DeviceChunk {
 // Text bytes per entry of the line directory: 256 → 1/64 of the text's size, ~6 newlines of a
 // 45-byte-line corpus per block, so the nine offsets extraction loads almost always decide.
 constexpr uint32_t LINE_BLOCK = 256;
+// Text bytes per line record (a 32-byte sector: entry start before the block, next newline after
+// it, 128-bit newline map): a quarter of the text's size, and extraction is one load per hit.
+constexpr uint32_t LINE_REC_BLOCK = 128;
 
 struct SearchTimes {
     float ms_bounds = 0.f, ms_extract = 0.f, ms_dedup = 0.f, ms_total = 0.f;
@@ -98,6 +102,8 @@ public:
     // Builds the line directory over a newline index: (*d_dir)[j] = newlines before text byte
     // j * LINE_BLOCK (cudaMalloc'ed here, owned by the caller).
     int build_line_directory(const uint32_t *d_nl, uint32_t n_lines, uint32_t n, uint32_t **d_dir);
+    // Builds the line records over a newline index (cudaMalloc'ed here, owned by the caller).
+    int build_line_records(const uint32_t *d_nl, uint32_t n_lines, uint32_t n, uint4 **d_rec);
 
     // Builds the 2-byte prefix table of a resident chunk: (*d_bucket)[a << 8 | b] = first SA slot
     // whose suffix starts with bytes a, b (entry 65536 = n).  A pattern of two or more bytes is

@@ -146,3 +146,66 @@ def test_line_directory_model_matches_reference_scans():
         assert dirv[-1] == len(nl)
         for pos in (range(n) if n <= 600 else rng.integers(0, n, size=600)):
             assert model_entry_bounds_dir(nl, dirv, n, int(pos)) == reference_entry_bounds(t, int(pos)), (n, int(pos))
+
+
+# ---- extraction through the line records (csrc/search.cu: line_records_kernel, entry_bounds_rec) ----
+LINE_REC_BLOCK = 128
+M64 = (1 << 64) - 1
+
+
+def model_line_records(nl, n):
+    """line_records_kernel: per 128-byte block (start of the entry open at its first byte, first
+    '\\n' at or after its end else n - 1, 128-bit newline map as two 64-bit halves)."""
+    recs = []
+    for j in range((n + LINE_REC_BLOCK - 1) // LINE_REC_BLOCK):
+        at, end = j * LINE_REC_BLOCK, (j + 1) * LINE_REC_BLOCK
+        lo = int(np.searchsorted(nl, at, side="left"))
+        open_at = int(nl[lo - 1]) + 1 if lo > 0 else 0
+        k, bm = lo, 0
+        while k < len(nl) and nl[k] < end:
+            bm |= 1 << int(nl[k] - at)
+            k += 1
+        nxt = int(nl[k]) if k < len(nl) else n - 1
+        recs.append((open_at, nxt, bm & M64, bm >> 64))
+    return recs
+
+
+def model_entry_bounds_rec(recs, pos):
+    blk, off = divmod(pos, LINE_REC_BLOCK)
+    open_at, nxt, lo64, hi64 = recs[blk]
+    base = blk * LINE_REC_BLOCK
+    f_lo = (lo64 & ((M64 << off) & M64)) if off < 64 else 0
+    f_hi = hi64 if off < 64 else (hi64 & ((M64 << (off - 64)) & M64))
+    e = nxt
+    if f_lo:
+        e = base + ((f_lo & -f_lo).bit_length() - 1)
+    elif f_hi:
+        e = base + 64 + ((f_hi & -f_hi).bit_length() - 1)
+    b_lo = ((lo64 & (M64 >> (64 - off))) if off else 0) if off < 64 else lo64
+    b_hi = (hi64 & (M64 >> (128 - off))) if off > 64 else 0
+    b = open_at
+    if b_hi:
+        b = base + 64 + b_hi.bit_length()
+    elif b_lo:
+        b = base + b_lo.bit_length()
+    return b, e
+
+
+def test_line_records_model_matches_reference_scans():
+    rng = np.random.default_rng(12)
+    texts = [b"\n" * 300, b"a" * 700, b"ab\n", b"x", b"\n", b"a" * 127 + b"\n" + b"b" * 200 + b"\n\n\n" + b"c" * 257,
+             b"a" * 63 + b"\n" + b"a" * 64 + b"\n" + b"a" * 63 + b"\n\n" + b"q" * 62 + b"\n"]
+    for p_nl in (0.5, 0.1, 0.02, 0.002):
+        for n in (1, 63, 64, 65, 127, 128, 129, 1000, 3000):
+            a = rng.integers(97, 100, size=n, dtype=np.uint8)
+            a[rng.random(n) < p_nl] = 10
+            texts.append(a.tobytes())
+            a2 = a.copy()
+            a2[-1] = 10
+            texts.append(a2.tobytes())
+    for t in texts:
+        n = len(t)
+        nl = np.flatnonzero(np.frombuffer(t, dtype=np.uint8) == 10).astype(np.int64)
+        recs = model_line_records(nl, n)
+        for pos in (range(n) if n <= 700 else rng.integers(0, n, size=700)):
+            assert model_entry_bounds_rec(recs, int(pos)) == reference_entry_bounds(t, int(pos)), (n, int(pos))

@@ -275,10 +275,11 @@ def test_search_random_patterns_vs_oracle(pss, oracle):
 
 @pytest.mark.parametrize("env", [{"PSS_BOUNDS_GROUP": "-4"}, {"PSS_BOUNDS_GROUP": "4"}, {"PSS_BOUNDS_GROUP": "-8"},
                                  {"PSS_BOUNDS_GROUP": "8"}, {"PSS_BOUNDS_GROUP": "-32"}, {"PSS_BOUNDS_GROUP": "32"},
-                                 {"PSS_LINE_DIR": "0"}])
+                                 {"PSS_LINE_DIR": "0"}, {"PSS_LINE_DIR": "1"}])
 def test_search_kernel_variants_vs_oracle(pss, oracle, env, monkeypatch):
     """The batched bounds kernel picks its geometry by batch size (a warp per pair below 16 384
-    pairs, 8 or 4 lanes per pair above) and extraction goes through the line directory; every
+    pairs, 8 or 4 lanes per pair above) and extraction reads the line records (PSS_LINE_DIR: 1 = the
+    line directory, 0 = text scans); every
     variant is forced here on the same patterns — empty, '\\n', longer than any window, absent,
     crossing entries — and compared with the oracle's ordered tuples."""
     for k, v in env.items():

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """A/B of the search kernels' variants on one config-3 chunk: PSS_LINE_DIR=0 (extraction scans
-the text) vs 1 (line directory), PSS_BOUNDS_GROUP=32 (one warp per pair) vs 16 / 8 lanes per
-pair.  Builds the chunk's suffix array once, opens the index once per variant and runs the same
+the text) vs 1 (line directory) vs 2 (line records); with PSS_AB_BOUNDS=1 instead the bounds
+kernel's geometries (PSS_BOUNDS_GROUP = lanes per pair, negative = no SA look-ahead).  Builds the chunk's suffix array once, opens the index once per variant and runs the same
 10 000-query batch (plus one high-hit bigram) through the C ABI, printing the stage times and
 checking that every variant returns identical tuples.  usage: search_ab.py [n_bytes] [repeat]"""
 import os
@@ -25,12 +25,9 @@ with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") els
     with open(p, "wb") as f:
         f.write(np.uint32(n).tobytes()); f.write(memoryview(text)); f.write(np.uint32(4 * n).tobytes()); f.write(memoryview(sa))
     results = {}
-    modes = [("dir1 g32", {"PSS_LINE_DIR": "1", "PSS_BOUNDS_GROUP": "32"}),
-             ("dir1 g32 no-lookahead", {"PSS_LINE_DIR": "1", "PSS_BOUNDS_GROUP": "-32"}),
-             ("dir1 g8", {"PSS_LINE_DIR": "1", "PSS_BOUNDS_GROUP": "8"}),
-             ("dir1 g8 no-lookahead", {"PSS_LINE_DIR": "1", "PSS_BOUNDS_GROUP": "-8"}),
-             ("dir1 g4", {"PSS_LINE_DIR": "1", "PSS_BOUNDS_GROUP": "4"}),
-             ("dir1 g4 no-lookahead", {"PSS_LINE_DIR": "1", "PSS_BOUNDS_GROUP": "-4"})]
+    modes = [("scan", {"PSS_LINE_DIR": "0"}), ("directory", {"PSS_LINE_DIR": "1"}), ("records", {"PSS_LINE_DIR": "2"})]
+    if os.environ.get("PSS_AB_BOUNDS"):
+        modes = [("g%s" % g, {"PSS_BOUNDS_GROUP": g}) for g in ("32", "-32", "8", "-8", "4", "-4")]
     for mode, env in modes:
         os.environ.update(env)
         r = pss.Reader(p)
