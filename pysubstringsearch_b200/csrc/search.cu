@@ -897,30 +897,57 @@ compact_kernel(const uint32_t *__restrict__ flag, const uint32_t *__restrict__ l
                uint32_t *__restrict__ pair_first, int32_t *__restrict__ out_chunk,
                uint32_t *__restrict__ out_start, uint32_t *__restrict__ out_end) {
     __shared__ uint32_t s_warp[CP_THREADS / 32];
+    // the tile's kept tuples, staged so that they leave the SM as one contiguous run per array
+    // (a thread's own tuples are 8 apart from its neighbour's: one sector per 4-byte store otherwise)
+    __shared__ uint32_t s_start[CP_TILE], s_end[CP_TILE];
+    __shared__ int32_t  s_chunk[CP_TILE];
     const uint32_t base = blockIdx.x * CP_TILE + threadIdx.x * CP_IPT;
-    uint32_t fl[CP_IPT];
+    uint32_t fl[CP_IPT], le[CP_IPT];
     uint32_t c = 0;
+    if (base + CP_IPT <= nhits) {
+        // 8 consecutive words, 32-byte aligned: two 16-byte loads per array
+        const uint4 f0 = __ldg(reinterpret_cast<const uint4 *>(flag + base)), f1 = __ldg(reinterpret_cast<const uint4 *>(flag + base) + 1);
+        const uint4 e0 = __ldg(reinterpret_cast<const uint4 *>(line_end + base)), e1 = __ldg(reinterpret_cast<const uint4 *>(line_end + base) + 1);
+        fl[0] = f0.x; fl[1] = f0.y; fl[2] = f0.z; fl[3] = f0.w; fl[4] = f1.x; fl[5] = f1.y; fl[6] = f1.z; fl[7] = f1.w;
+        le[0] = e0.x; le[1] = e0.y; le[2] = e0.z; le[3] = e0.w; le[4] = e1.x; le[5] = e1.y; le[6] = e1.z; le[7] = e1.w;
+    } else {
 #pragma unroll
-    for (int e = 0; e < CP_IPT; ++e) {
-        fl[e] = (base + e < nhits) ? flag[base + e] : 0u;
-        c += fl[e] >> 31;
-    }
-    uint32_t total;
-    uint32_t o = block_excl_sum_256(c, s_warp, &total) + tile_prefix[blockIdx.x];
-    if (base >= nhits) return;
-    uint32_t p = find_pair(hit_off, npairs, base + hit_base);
-#pragma unroll
-    for (int e = 0; e < CP_IPT; ++e) {
-        const uint32_t f = base + e;
-        if (f >= nhits) break;
-        while (f + hit_base >= __ldg(hit_off + p + 1)) ++p;           // skips pairs without hits
-        if (f + hit_base == __ldg(hit_off + p)) pair_first[p] = o;    // first hit of pair p: its output offset
-        if (fl[e] >> 31) {
-            out_chunk[o] = chunks[(pair_base + p) % (uint32_t)nc].global_id;
-            out_start[o] = fl[e] & 0x7FFFFFFFu;
-            out_end[o]   = line_end[f];
-            ++o;
+        for (int e = 0; e < CP_IPT; ++e) {
+            fl[e] = (base + e < nhits) ? flag[base + e] : 0u;
+            le[e] = (base + e < nhits) ? line_end[base + e] : 0u;
         }
+    }
+#pragma unroll
+    for (int e = 0; e < CP_IPT; ++e) c += fl[e] >> 31;
+    uint32_t total;
+    const uint32_t local = block_excl_sum_256(c, s_warp, &total);
+    const uint32_t tile_o = tile_prefix[blockIdx.x];
+    if (base < nhits) {
+        uint32_t o = local;
+        uint32_t p = find_pair(hit_off, npairs, base + hit_base);
+        int32_t  gid = chunks[(pair_base + p) % (uint32_t)nc].global_id;
+#pragma unroll
+        for (int e = 0; e < CP_IPT; ++e) {
+            const uint32_t f = base + e;
+            if (f >= nhits) break;
+            if (f + hit_base >= __ldg(hit_off + p + 1)) {
+                do { ++p; } while (f + hit_base >= __ldg(hit_off + p + 1));       // skips pairs without hits
+                gid = chunks[(pair_base + p) % (uint32_t)nc].global_id;
+            }
+            if (f + hit_base == __ldg(hit_off + p)) pair_first[p] = tile_o + o;   // first hit of pair p: its output offset
+            if (fl[e] >> 31) {
+                s_chunk[o] = gid;
+                s_start[o] = fl[e] & 0x7FFFFFFFu;
+                s_end[o]   = le[e];
+                ++o;
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < total; t += CP_THREADS) {
+        out_chunk[tile_o + t] = s_chunk[t];
+        out_start[tile_o + t] = s_start[t];
+        out_end[tile_o + t]   = s_end[t];
     }
 }
 
