@@ -550,7 +550,10 @@ def run_ours(args):
             "roofline": {"bound": "hbm-random", "unit": "GB/s",
                          "algorithmic_bytes": "2 x ceil(log2 n) probes x (one 32 B SA sector + one 32 B text sector) per (query, chunk)",
                          "achieved": npairs_busiest * probe_bytes / (dev_stage["bounds"] * 1e-3) / 1e9 if dev_stage["bounds"] else None,
-                         "kernel": "bounds_kernel", "peak": peak,
+                         "kernel": "bounds_group_kernel (4 or 8 lanes per pair from 16 384 pairs per rank on) / bounds_kernel (a warp per pair)",
+                         "peak": peak,
+                         "note": "random 32-byte sectors: a fraction of the streaming peak is the ceiling; "
+                                 "profiles/r02_search_bounds_ab.txt has the geometry sweep",
                          "ncu": "profiles/r02_ncu_search_kernels.txt (sectors per request, DRAM bytes)"},
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
