@@ -387,6 +387,40 @@ def run_ours(args):
     dev_stage = {"bounds": float(dres.ms_bounds), "extract": float(dres.ms_extract), "dedup": float(dres.ms_dedup),
                  "exchange": exch_ms / K}
 
+    # ---- the same search with a 10x larger batch (the 10 000 queries ten times over): per-batch
+    #      fixed costs (launches, the collectives' latency, scalar read-backs) stop hiding how the
+    #      per-chunk work itself scales over the ranks ---------------------------------------------
+    big = None
+    if args.big_batch > 1:
+        nbig = len(pats) * args.big_batch
+        big_total = int(offs[-1]) * args.big_batch
+        if rank == 0:
+            lens = np.diff(offs)
+            big_offs = np.zeros(nbig + 1, dtype=np.int64)
+            np.cumsum(np.tile(lens, args.big_batch), out=big_offs[1:])
+            d_big_blob = torch.from_numpy(np.tile(blob[:int(offs[-1])], args.big_batch)).to(dev)
+            d_big_offs = torch.from_numpy(big_offs).to(dev)
+        bres = pss.DeviceResult()
+
+        def search_big():
+            pss.check(lib.pss_reader_search_batch_dist_device(
+                reader.h, comm.h, d_big_blob.data_ptr() if rank == 0 else None, d_big_offs.data_ptr() if rank == 0 else None,
+                nbig, big_total, C.byref(bres)))
+            return int(bres.n_entries)
+
+        for _ in range(2):
+            search_big()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            big_entries = search_big()
+        barrier()
+        big_s = max_over_ranks((time.perf_counter() - t0) / 3)
+        big = {"queries": nbig, "value": nbig / big_s, "unit": "queries/s", "ms_per_batch": big_s * 1e3,
+               "entries": big_entries, "what": "the %d queries x %d in one batch, device-resident, same exchange" % (len(pats), args.big_batch)}
+        if rank == 0:
+            del d_big_blob, d_big_offs
+
     # ---- end-to-end through the C-ABI host seams (pinned host buffers) ------------------------
     def e2e_build():
         """Host text → host suffix array for every owned chunk: all builds are queued at once
@@ -546,6 +580,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": h2d_search, "d2h_bytes_per_step": d2h_search, "entries": int(n_e2e_entries),
                     "steps": Ke, "api": "pss_reader_search_batch_dist (host patterns → host tuples on rank 0)"},
             "stage_ms_rank0": dev_stage,
+            "big_batch": big,
             "e2e_stage_ms_rank0": sstats,
             "roofline": {"bound": "hbm-random", "unit": "GB/s",
                          "algorithmic_bytes": "2 x ceil(log2 n) probes x (one 32 B SA sector + one 32 B text sector) per (query, chunk)",
@@ -591,6 +626,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=synth.CONFIG3_CHUNKS, help="chunks of the index (default 15), chunk k -> rank k %% N")
     ap.add_argument("--queries", type=int, default=N_QUERIES)
     ap.add_argument("--e2e-steps", type=int, default=5, help="timed steps of the host-to-host legs (<= --steps)")
+    ap.add_argument("--big-batch", type=int, default=10, help="extra search measurement with the query list repeated this many times in one batch (<= 1: off)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-python", action="store_true")
     ap.add_argument("--skip-writer", action="store_true")

@@ -17,10 +17,19 @@ with tempfile.TemporaryDirectory() as d:
     for e in bytes(text).split(b"\n")[:-1]:
         w.add_entry(e)
     w.close()
-    r, o = pss.Reader(p), O.Reader(p)
-    for pats in ([b"ab"], [b""], [b"e ", b"zz", b"\n"], [bytes(text[k:k + 7]) for k in range(0, 40000, 400)]):
-        qo, ch, st, en, _ = r.search_batch(pats)
-        c, och, ost, oen = o.search_multiple_tuples(pats)
-        assert np.array_equal(ch, och) and np.array_equal(st, ost) and np.array_equal(en, oen)
-    r.close()
+    o = O.Reader(p)
+    batches = ([b"ab"], [b""], [b"e ", b"zz", b"\n"], [bytes(text[k:k + 7]) for k in range(0, 40000, 400)])
+    want = [o.search_multiple_tuples(pats) for pats in batches]
+    # every geometry of the bounds kernel (a warp per pair, 8 / 4 lanes per pair, with and without the
+    # SA look-ahead) and every extraction mode (line records, line directory, text scans)
+    for env in ({}, {"PSS_BOUNDS_GROUP": "-4"}, {"PSS_BOUNDS_GROUP": "8"}, {"PSS_BOUNDS_GROUP": "-32"},
+                {"PSS_LINE_DIR": "1"}, {"PSS_LINE_DIR": "0"}, {"PSS_SMALL_PATH": "0"}):
+        for k in ("PSS_BOUNDS_GROUP", "PSS_LINE_DIR", "PSS_SMALL_PATH"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        r = pss.Reader(p)
+        for pats, (c, och, ost, oen) in zip(batches, want):
+            qo, ch, st, en, _ = r.search_batch(pats)
+            assert np.array_equal(ch, och) and np.array_equal(st, ost) and np.array_equal(en, oen), env
+        r.close()
 print("sanitize_check ok")
