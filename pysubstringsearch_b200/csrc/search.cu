@@ -1553,7 +1553,9 @@ int Searcher::ensure_heavy(int64_t n) {
 }
 
 // Output arrays for `entries` tuples; what is already there is kept (sub-batches append).
-int Searcher::ensure_out(int64_t entries, cudaStream_t s) {
+// Room for `entries` result tuples; the first `keep` (the entries earlier sub-batches of this
+// batch have produced) survive a regrowth, nothing else is copied.
+int Searcher::ensure_out(int64_t entries, int64_t keep, cudaStream_t s) {
     if (entries <= out_cap_) return PSS_OK;
     int64_t cap = std::max<int64_t>(entries + entries / 4, 1 << 16);
     int32_t  *nc = nullptr;
@@ -1561,12 +1563,13 @@ int Searcher::ensure_out(int64_t entries, cudaStream_t s) {
     PSS_CUDA_TRY(cudaMalloc(&nc, cap * sizeof(int32_t)));
     PSS_CUDA_TRY(cudaMalloc(&ns, cap * sizeof(uint32_t)));
     PSS_CUDA_TRY(cudaMalloc(&ne, cap * sizeof(uint32_t)));
-    if (out_cap_) {
-        PSS_CUDA_TRY(cudaMemcpyAsync(nc, d_out_chunk_, out_cap_ * 4, cudaMemcpyDeviceToDevice, s));
-        PSS_CUDA_TRY(cudaMemcpyAsync(ns, d_out_start_, out_cap_ * 4, cudaMemcpyDeviceToDevice, s));
-        PSS_CUDA_TRY(cudaMemcpyAsync(ne, d_out_end_, out_cap_ * 4, cudaMemcpyDeviceToDevice, s));
-        PSS_CUDA_TRY(cudaStreamSynchronize(s));
+    keep = std::min(keep, out_cap_);
+    if (keep > 0) {
+        PSS_CUDA_TRY(cudaMemcpyAsync(nc, d_out_chunk_, keep * 4, cudaMemcpyDeviceToDevice, s));
+        PSS_CUDA_TRY(cudaMemcpyAsync(ns, d_out_start_, keep * 4, cudaMemcpyDeviceToDevice, s));
+        PSS_CUDA_TRY(cudaMemcpyAsync(ne, d_out_end_, keep * 4, cudaMemcpyDeviceToDevice, s));
     }
+    if (out_cap_) PSS_CUDA_TRY(cudaStreamSynchronize(s));   // nothing queued may still use the old arrays
     cudaFree(d_out_chunk_); cudaFree(d_out_start_); cudaFree(d_out_end_);
     d_out_chunk_ = nc; d_out_start_ = ns; d_out_end_ = ne;
     out_cap_ = cap;
@@ -1734,7 +1737,7 @@ int Searcher::search(const uint8_t *d_patterns, const int64_t *d_offsets, int32_
     for (const Sub &sb : subs) {
         PSS_TRY(ensure_hits(sb.nh));
         if ((int64_t)entries + sb.nh >= (1ll << 32)) return fail(PSS_ERR_ARG, "more than 2^32 entries in one batch");
-        if (!defer) PSS_TRY(ensure_out((int64_t)entries + sb.nh, s));   // entries <= matching suffixes: no count needed up front
+        if (!defer) PSS_TRY(ensure_out((int64_t)entries + sb.nh, entries, s));   // entries <= matching suffixes: no count needed up front
         const uint32_t *hit_off = d_hit_off_ + sb.a, *heavy_off = d_heavy_off_ + sb.a;
         const uint32_t hit_base = 0;                         // offsets are relative to the sub-batch
         uint32_t n_heavy = sb.n_heavy, n_medium = sb.n_medium;

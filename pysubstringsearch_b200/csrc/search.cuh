@@ -138,7 +138,7 @@ private:
     int ensure_pairs(int64_t npairs, int64_t nq);
     int ensure_hits(int64_t nhits);
     int ensure_heavy(int64_t n);
-    int ensure_out(int64_t entries, cudaStream_t s);
+    int ensure_out(int64_t entries, int64_t keep, cudaStream_t s);
 
     int          device_ = -1;
     cudaStream_t stream_ = nullptr;
