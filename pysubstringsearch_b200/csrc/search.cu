@@ -95,7 +95,7 @@ bounds_kernel(const DeviceChunk *__restrict__ chunks, int nc, const uint8_t *__r
               const int64_t *__restrict__ pat_off, uint32_t npairs, uint32_t *__restrict__ lb_out,
               uint32_t *__restrict__ cnt_out) {
     const uint32_t lane = lane_id();
-    const uint32_t pair = (blockIdx.x * BD_THREADS + threadIdx.x) >> 5;
+    const uint32_t pair = (uint32_t)(((uint64_t)blockIdx.x * BD_THREADS + threadIdx.x) >> 5);   // up to 2^31 pairs x 32 lanes
     if (pair >= npairs) return;
     const uint32_t q = pair / (uint32_t)nc, c = pair % (uint32_t)nc;
     uint32_t lb, cnt;
@@ -125,7 +125,7 @@ bounds_group_kernel(const DeviceChunk *__restrict__ chunks, int nc, const uint8_
     const uint32_t lane   = lane_id();
     const uint32_t sub    = lane % G;              // byte of the window this lane owns
     const uint32_t gbase  = lane - sub;            // first lane of the group
-    const uint32_t pair   = (blockIdx.x * BD_THREADS + threadIdx.x) / G;
+    const uint32_t pair   = (uint32_t)(((uint64_t)blockIdx.x * BD_THREADS + threadIdx.x) / G);   // up to 2^31 pairs x G lanes
     const bool     valid  = pair < npairs;
     const uint32_t q = valid ? pair / (uint32_t)nc : 0u, c = valid ? pair % (uint32_t)nc : 0u;
     const uint8_t *__restrict__ text = chunks[c].text;
