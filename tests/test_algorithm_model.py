@@ -209,3 +209,92 @@ def test_line_records_model_matches_reference_scans():
         recs = model_line_records(nl, n)
         for pos in (range(n) if n <= 700 else rng.integers(0, n, size=700)):
             assert model_entry_bounds_rec(recs, int(pos)) == reference_entry_bounds(t, int(pos)), (n, int(pos))
+
+
+# ---- Writer.add_entries_from_file_lines: bulk append of whole runs of lines (csrc/host_index.cu) ----
+def model_ingest_chunks(data, capacity, block=1 << 20):
+    """Statement-for-statement model of pss_writer_add_entries_from_file_lines + finalize: returns
+    the chunk texts in order.  A run of complete records without '\\r' that fits the room left is
+    appended with one copy; everything else goes record by record through the reference's flush
+    rule `len + entry + 1 > capacity` (lib.rs:75) with Rust's Vec growth of the logical capacity."""
+    chunks, text, line = [], bytearray(), bytearray()
+    cap = [capacity]
+
+    def dump():
+        if text:
+            chunks.append(bytes(text))
+            text.clear()
+
+    def reserve_logical(additional):
+        if cap[0] - len(text) >= additional:
+            return
+        cap[0] = max(max(cap[0] * 2, len(text) + additional), 8)
+
+    def emit(rec, terminated):
+        if terminated and rec.endswith(b"\r"):
+            rec = rec[:-1]
+        if len(text) + len(rec) + 1 > cap[0]:
+            dump()
+        reserve_logical(len(rec))
+        text.extend(rec)
+        reserve_logical(1)
+        text.extend(b"\n")
+
+    for at in range(0, len(data), block):
+        b = data[at:at + block]
+        frm, no_cr = 0, b"\r" not in b
+        while True:
+            if no_cr and not line and len(text) < cap[0]:
+                room = min(cap[0] - len(text), len(b) - frm)
+                last = b.rfind(b"\n", frm, frm + room)
+                if last >= 0:
+                    text.extend(b[frm:last + 1])
+                    frm = last + 1
+            nl = b.find(b"\n", frm)
+            if nl < 0:
+                break
+            if not line:
+                emit(b[frm:nl], True)
+            else:
+                line.extend(b[frm:nl])
+                emit(bytes(line), True)
+                line.clear()
+            frm = nl + 1
+        line.extend(b[frm:])
+    if line:
+        emit(bytes(line), False)
+    dump()
+    return chunks
+
+
+def _container_chunk_texts(path):
+    raw, out, pos = open(path, "rb").read(), [], 0
+    while pos < len(raw):
+        n = int.from_bytes(raw[pos:pos + 4], "little")
+        out.append(raw[pos + 4:pos + 4 + n])
+        pos += 8 + 5 * n
+    return out
+
+
+def test_bulk_ingestion_model_matches_oracle_writer(tmp_path):
+    """The bulk path must cut chunks exactly where the reference's per-line loop does: compared
+    with the oracle Writer (restatement of lib.rs:67-86) on LF, CRLF and mixed files, chunk sizes
+    below / around / above the read block, over-long lines, and a missing final newline."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(5)
+    words = [bytes(rng.integers(97, 123, size=int(rng.integers(1, 9)), dtype=np.uint8)) for _ in range(200)]
+
+    def lines(k, sep):
+        return sep.join(b" ".join(words[int(j)] for j in rng.integers(0, 200, size=int(rng.integers(0, 12)))) for _ in range(k))
+
+    files = [lines(3000, b"\n") + b"\n", lines(3000, b"\n"), lines(2000, b"\r\n") + b"\r\n",
+             lines(1500, b"\n") + b"\r\n" + lines(1500, b"\n") + b"\n", b"", b"\n", b"x", b"\n\n\n",
+             lines(500, b"\n") + b"\n" + b"q" * 5000 + b"\n" + lines(500, b"\n") + b"\n", b"a\rb\n" + lines(100, b"\n")]
+    src, idx = str(tmp_path / "in.txt"), str(tmp_path / "o.idx")
+    for data in files:
+        for capacity, block in ((64, 256), (1000, 256), (1000, 4096), (4096, 1000), (100_000, 1 << 14), (1 << 20, 1 << 20)):
+            open(src, "wb").write(data)
+            w = O.Writer(idx, capacity)
+            w.add_entries_from_file_lines(src)
+            w.close()
+            assert model_ingest_chunks(data, capacity, block) == _container_chunk_texts(idx), (len(data), capacity, block)
