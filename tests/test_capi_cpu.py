@@ -173,3 +173,33 @@ int main(void) {
             assert getattr(mirrors[struct], field).offset == int(val), key
         else:
             assert C.sizeof(mirrors[key]) == int(val), key
+
+
+def test_header_is_plain_c_and_static_archive_links(tmp_path):
+    """include/pss.h must stay bindable from C / Rust (plain C99, no C++), and the static archive a
+    build.rs would link (`make static`) must resolve with nothing but the
+    static CUDA runtime: a C program is compiled against the header with -pedantic, linked against
+    libpss_b200.a and run (no GPU needed for pss_version / a failing pss_reader_open)."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "pysubstringsearch_b200", "csrc")
+    subprocess.check_call(["make", "-C", csrc, "static"], stdout=subprocess.DEVNULL)
+    cuda_lib = os.path.join(os.path.dirname(os.path.dirname(shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc")), "lib64")
+    src = tmp_path / "smoke.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "pss.h"\n'
+        'int main(void) {\n'
+        '    pss_reader *r = 0;\n'
+        '    int rc = pss_reader_open("/nonexistent/file.idx", &r);\n'
+        '    printf("%s|%d|%s\\n", pss_version(), rc, pss_last_error());\n'
+        '    return 0;\n}\n')
+    obj, exe = str(tmp_path / "smoke.o"), str(tmp_path / "smoke")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                           "-c", str(src), "-o", obj])
+    subprocess.check_call(["g++", obj, "-L", os.path.join(root, "pysubstringsearch_b200"), "-l:libpss_b200.a",
+                           "-L", cuda_lib, "-lcudart_static", "-lpthread", "-ldl", "-lrt", "-o", exe])
+    out = subprocess.check_output([exe]).decode().strip().split("|")
+    assert "sm_100a" in out[0] and int(out[1]) != 0 and "No such file" in out[2]
+    needed = subprocess.check_output(["ldd", exe]).decode()
+    assert "libcudart" not in needed and "libpss" not in needed      # everything CUDA-side is inside the binary
