@@ -203,3 +203,21 @@ def test_header_is_plain_c_and_static_archive_links(tmp_path):
     assert "sm_100a" in out[0] and int(out[1]) != 0 and "No such file" in out[2]
     needed = subprocess.check_output(["ldd", exe]).decode()
     assert "libcudart" not in needed and "libpss" not in needed      # everything CUDA-side is inside the binary
+
+
+def test_libsais_named_shim_forwards_the_contract():
+    """The optional shim exports the reference's own foreign symbol `libsais` (lib.rs:14-22): same
+    argument contract as pss_libsais, checked here without a GPU; with one it must build the same
+    suffix array (tests/test_gpu_parity.py::test_libsais_shim_on_gpu)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-C", os.path.join(root, "pysubstringsearch_b200", "csrc"), "shim"], stdout=subprocess.DEVNULL)
+    shim = C.CDLL(os.path.join(root, "pysubstringsearch_b200", "libsais_pss_shim.so"))
+    shim.libsais.restype = C.c_int32
+    shim.libsais.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    buf = (C.c_uint8 * 4)()
+    sa = (C.c_int32 * 4)()
+    assert shim.libsais(None, None, 5, 0, None) == -1
+    assert shim.libsais(buf, sa, -1, 0, None) == -1
+    assert shim.libsais(buf, sa, 4, -1, None) == -1
+    assert shim.libsais(buf, sa, 0, 0, None) == 0

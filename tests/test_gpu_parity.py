@@ -111,6 +111,22 @@ def test_sa_larger_vs_reference_libsais(pss, oracle):
         assert np.array_equal(pss.libsais(t), ref(t))
 
 
+def test_libsais_shim_on_gpu(pss, oracle):
+    """libsais_pss_shim.so: the symbol `libsais` itself (what src/lib.rs:14-22 declares), forwarding
+    to pss_libsais."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "pysubstringsearch_b200", "libsais_pss_shim.so")
+    if not os.path.exists(path):
+        pytest.skip("shim not built (make -C pysubstringsearch_b200/csrc shim)")
+    shim = C.CDLL(path)
+    shim.libsais.restype = C.c_int32
+    shim.libsais.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    t = synth.zipf_words_text(200_000, seed=77, vocab=1024, block=1 << 14)
+    sa = np.empty(len(t), dtype=np.int32)
+    assert shim.libsais(t.ctypes.data, sa.ctypes.data, len(t), 0, None) == 0
+    assert np.array_equal(sa, oracle.suffix_array_port(t))
+
+
 def test_libsais_freq_table(pss):
     t = np.frombuffer(b"abracadabra\n", dtype=np.uint8)
     sa = np.empty(len(t), dtype=np.int32)
