@@ -93,6 +93,7 @@ def test_new_entry_points_check_their_arguments(pss):
         assert pss.lib.pss_comm_create(None, 0, 1, C.byref(h)) == -3
 
 
+@pytest.mark.filterwarnings("ignore::pytest.PytestUnraisableExceptionWarning")   # a Writer with buffered entries is dropped without a GPU
 def test_python_module_surface():
     import pysubstringsearch
     import pysubstringsearch_b200 as m
@@ -113,6 +114,18 @@ def test_python_module_surface():
             w.add_entry(text=b"ab")
         with pytest.raises(FileNotFoundError):
             w.add_entries_from_file_lines(input_file_path=os.path.join(d, "nope.txt"))
+        # add_entry uses the vectorcall convention with a fast path for add_entry(s) / add_entry(text=s);
+        # every other call shape must still fail like the generic parser.  (The entries stay buffered:
+        # nothing is flushed here, and the failing close at teardown — no GPU — is reported, not raised.)
+        big = m.Writer(index_file_path=os.path.join(d, "b.idx"), max_chunk_len=1 << 20)
+        big.writer.add_entry("positional")
+        big.writer.add_entry(text="keyword")
+        big.add_entry("façade, non-ASCII ✓")
+        for bad in (lambda: big.writer.add_entry(), lambda: big.writer.add_entry(b"bytes"), lambda: big.writer.add_entry(txt="x"),
+                    lambda: big.writer.add_entry("a", "b"), lambda: big.writer.add_entry("a", text="b"),
+                    lambda: big.writer.add_entry(text="a", other=1)):
+            with pytest.raises(TypeError):
+                bad()
 
 
 def test_product_never_imports_oracle():
